@@ -1,0 +1,353 @@
+// tcgen05 implicit-GEMM kernel: one kernel serves the all-pairs correlation (a 1x1 "conv" whose
+// weights are the other image's features) and every stride-1 convolution of the update blocks.
+//
+//   D[128 px, bn cout] = sum over (tap, 64-channel chunk) of  A_tap[128 px, 64] * W_tap[bn, 64]^T
+//
+// * A operand: a TH x TW pixel patch of an NHWC fp16 activation plane, fetched by ONE 4-D TMA box per
+//   (tap, chunk) at coordinates shifted by the tap offset; out-of-image rows/cols are zero-filled by
+//   the TMA unit, which *is* Keras 'same' padding -- no im2col buffer, no halo logic.
+// * B operand: packed weights [tap][cout][cin] fp16, one 3-D TMA box per (tap, chunk).
+// * Both operands land in shared memory K-major with the 128-byte swizzle and are consumed in place
+//   by tcgen05.mma (kind::f16, M=128, N=bn, K=16); the fp32 accumulator lives in TMEM.
+// * fp32-grade arithmetic from fp16 tensor cores: each operand is a (hi, lo) fp16 pair and every
+//   K step issues hi*hi, lo*hi, hi*lo into the same accumulator (DESIGN.md "Precision").
+// * Warp roles: warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA issuer (one
+//   elected lane), warps 2..5 = epilogue (TMEM -> registers -> fused bias / activation / GRU gating /
+//   hi-lo re-split -> global).  smem full/empty mbarrier ring between producer and issuer,
+//   tcgen05.commit -> mbarrier between issuer and epilogue.
+#pragma once
+#include "common.cuh"
+#include "tmap.cuh"
+
+namespace raft {
+
+enum TcEpilogue : int {
+  EPI_LINEAR = 0,  // v = act(acc*inv_scale + bias) * out_scale  -> optional fp32 and/or fp16 hi/lo planes
+  EPI_GRU_ZR = 1,  // cols [0,hid): z = sigmoid(v) -> z plane; cols [hid,2hid): r = sigmoid(v), r*h -> hi/lo planes
+  EPI_GRU_Q = 2,   // q = tanh(v); h = (1-z)*h + z*q -> h fp32 (in place) + hi/lo planes
+  EPI_CORR = 3,    // v = acc / sqrt(C) -> fp32 pyramid level rows
+};
+enum TcAct : int { ACT_NONE = 0, ACT_RELU = 1 };
+
+constexpr int kTcThreads = 192;
+constexpr int kTileM = 128;
+constexpr int kChunkK = 64;                       // fp16 elements per 128-byte swizzled row
+constexpr int kABytes = kTileM * kChunkK * 2;     // 16 KiB per A plane per stage
+constexpr int kSmemBudget = 227 * 1024 - 2048;
+
+struct alignas(64) TcConvParams {
+  CUtensorMap a_hi[2], a_lo[2];   // up to two channel-concatenated source tensors (K segments)
+  CUtensorMap b_hi, b_lo;
+  int nseg, seg_chunks[2], seg_c0[2];
+  int kh, kw, ph, pw;             // taps and 'same' padding (pad before)
+  int B, H, W, TH, TW, tiles_x, tiles_y;
+  int bn, n_total;                // N per CTA (multiple of 16, <= 256); total valid output columns
+  int nstages, stage_bytes, tmem_cols;
+  int b_batch_stride;             // B-map coordinate 2 = tap + b * b_batch_stride (correlation: 1, taps = 1)
+  int mode, act;
+  const float* bias;              // [n_total padded to bn multiple]; may be null
+  const float* inv_scale;         // device scalar: 1 / (2^k weight scale); may be null (=1)
+  float out_scale;                // applied after the activation (0.25 for the mask head)
+  float corr_div;                 // EPI_CORR: sqrt(C)
+  float* out_f32; int f32_stride, f32_c0;
+  __half* out_hi; __half* out_lo; int h_stride, h_c0;
+  const float* concat_src; int concat_n;   // EPI_LINEAR: fp32 (px, concat_n) appended at columns [n_total, n_total+concat_n)
+  float* z; int hid;                       // GRU: z plane (px, hid) fp32
+  float* h;                                // GRU: hidden state (px, hid) fp32, updated in place by EPI_GRU_Q
+};
+
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void store_f32x32(float* dst, const float (&v)[32], int nvalid, bool vec_ok) {
+  if (nvalid >= 32 && vec_ok) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < nvalid) dst[j] = v[j];
+  }
+}
+__device__ __forceinline__ void store_split32(__half* dhi, __half* dlo, const float (&v)[32]) {
+  uint32_t ph[16], pl[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    __half h0, l0, h1, l1;
+    split_f16(v[2 * j], h0, l0);
+    split_f16(v[2 * j + 1], h1, l1);
+    ph[j] = pack_h2(h0, h1);
+    pl[j] = pack_h2(l0, l1);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    reinterpret_cast<uint4*>(dhi)[j] = make_uint4(ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
+    reinterpret_cast<uint4*>(dlo)[j] = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+  }
+}
+#endif
+
+__global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_constant__ TcConvParams p) {
+#if defined(__CUDA_ARCH__)
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int nst = p.nstages;
+  const int b_bytes = p.bn * kChunkK * 2;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)nst * p.stage_bytes);
+  uint64_t* empty_bar = full_bar + nst;
+  uint64_t* accum_bar = empty_bar + nst;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // tile coordinates
+  int mt = blockIdx.x;
+  const int tx = mt % p.tiles_x;
+  mt /= p.tiles_x;
+  const int ty = mt % p.tiles_y;
+  const int b = mt / p.tiles_y;
+  const int x0 = tx * p.TW, y0 = ty * p.TH;
+  const int n0 = blockIdx.y * p.bn;
+  const int ntaps = p.kh * p.kw;
+  const int chunks_per_tap = p.seg_chunks[0] + (p.nseg > 1 ? p.seg_chunks[1] : 0);
+  const int total = ntaps * chunks_per_tap;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < nst; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_mbar_init();
+    prefetch_tmap(&p.a_hi[0]);
+    prefetch_tmap(&p.a_lo[0]);
+    prefetch_tmap(&p.b_hi);
+    prefetch_tmap(&p.b_lo);
+    if (p.nseg > 1) {
+      prefetch_tmap(&p.a_hi[1]);
+      prefetch_tmap(&p.a_lo[1]);
+    }
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_holder, (uint32_t)p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int it = 0;
+      for (int tap = 0; tap < ntaps; ++tap) {
+        const int dy = tap / p.kw - p.ph, dx = tap % p.kw - p.pw;
+        int kc = 0;
+        for (int seg = 0; seg < p.nseg; ++seg) {
+          for (int ch = 0; ch < p.seg_chunks[seg]; ++ch, ++kc, ++it) {
+            const int s = it % nst;
+            const uint32_t phase = (uint32_t)(it / nst) & 1u;
+            mbar_wait(&empty_bar[s], phase ^ 1u);
+            uint8_t* st = smem + (size_t)s * p.stage_bytes;
+            mbar_arrive_expect_tx(&full_bar[s], (uint32_t)p.stage_bytes);
+            const int c = p.seg_c0[seg] + ch * kChunkK;
+            tma_load_4d(st, &p.a_hi[seg], &full_bar[s], c, x0 + dx, y0 + dy, b);
+            tma_load_4d(st + kABytes, &p.a_lo[seg], &full_bar[s], c, x0 + dx, y0 + dy, b);
+            const int tcoord = tap + b * p.b_batch_stride;
+            tma_load_3d(st + 2 * kABytes, &p.b_hi, &full_bar[s], kc * kChunkK, n0, tcoord);
+            tma_load_3d(st + 2 * kABytes + b_bytes, &p.b_lo, &full_bar[s], kc * kChunkK, n0, tcoord);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = make_idesc_f16(kTileM, p.bn);
+    for (int it = 0; it < total; ++it) {
+      const int s = it % nst;
+      const uint32_t phase = (uint32_t)(it / nst) & 1u;
+      mbar_wait(&full_bar[s], phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sa = smem_u32(smem + (size_t)s * p.stage_bytes);
+        const uint64_t a_hi = make_desc_sw128(sa);
+        const uint64_t a_lo = make_desc_sw128(sa + kABytes);
+        const uint64_t b_hi = make_desc_sw128(sa + 2 * kABytes);
+        const uint64_t b_lo = make_desc_sw128(sa + 2 * kABytes + b_bytes);
+#pragma unroll
+        for (int k = 0; k < kChunkK / 16; ++k)   // +32 bytes per K=16 step == +2 in 16-byte units
+          umma_f16(tmem_base, a_hi + 2 * k, b_hi + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < kChunkK / 16; ++k) umma_f16(tmem_base, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+#pragma unroll
+        for (int k = 0; k < kChunkK / 16; ++k) umma_f16(tmem_base, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+        umma_commit(&empty_bar[s]);                 // frees the smem slot once these MMAs retire
+        if (it == total - 1) umma_commit(accum_bar);  // accumulator complete -> epilogue
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
+    const int m = quarter * 32 + lane;               // tile row == TMEM lane
+    const int xl = m % p.TW, yl = m / p.TW;
+    const int x = x0 + xl, y = y0 + yl;
+    const bool valid = (x < p.W) && (y < p.H);
+    const size_t pix = ((size_t)b * p.H + (valid ? y : 0)) * p.W + (valid ? x : 0);
+    const float inv_scale = p.inv_scale ? __ldg(p.inv_scale) : 1.0f;
+
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
+
+    for (int c0 = 0; c0 < p.bn; c0 += 32) {
+      const int ncol = min(32, p.bn - c0);           // bn is a multiple of 16: 32 or 16
+      uint32_t r[32];
+      if (ncol == 32) {
+        tmem_ld_32x32(trow + (uint32_t)c0, r);
+      } else {
+        uint32_t r16[16];
+        tmem_ld_32x16(trow + (uint32_t)c0, r16);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[j] = r16[j];
+#pragma unroll
+        for (int j = 16; j < 32; ++j) r[j] = 0u;
+      }
+      tmem_ld_wait();
+      if (!valid) continue;
+      const int col = n0 + c0;                       // first global output column of this chunk
+      float v[32];
+
+      if (p.mode == EPI_CORR) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __fdiv_rn(__uint_as_float(r[j]), p.corr_div);
+        const int nvalid = min(ncol, p.n_total - col);
+        if (nvalid > 0) {
+          float* dst = p.out_f32 + pix * (size_t)p.f32_stride + col;
+          store_f32x32(dst, v, nvalid, (p.f32_stride & 3) == 0);
+        }
+        continue;
+      }
+
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float t = __uint_as_float(r[j]) * inv_scale;
+        if (p.bias) t += __ldg(p.bias + col + j);
+        v[j] = t;
+      }
+
+      if (p.mode == EPI_LINEAR) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float t = v[j];
+          if (p.act == ACT_RELU) t = fmaxf(t, 0.0f);
+          t *= p.out_scale;
+          if (col + j >= p.n_total) {                // padded columns: concat tail, else exact zeros
+            const int cj = col + j - p.n_total;
+            t = (p.concat_src && cj < p.concat_n) ? __ldg(p.concat_src + pix * p.concat_n + cj) : 0.0f;
+          }
+          v[j] = t;
+        }
+        if (p.out_f32) {
+          const int nvalid = min(ncol, p.n_total - col);
+          if (nvalid > 0)
+            store_f32x32(p.out_f32 + pix * (size_t)p.f32_stride + p.f32_c0 + col, v, nvalid,
+                         ((p.f32_stride | p.f32_c0) & 3) == 0);
+        }
+        if (p.out_hi) {
+          const size_t o = pix * (size_t)p.h_stride + p.h_c0 + col;
+          store_split32(p.out_hi + o, p.out_lo + o, v);
+        }
+      } else if (p.mode == EPI_GRU_ZR) {
+        if (col < p.hid) {                            // z gate
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = sigmoidf_acc(v[j]);
+          store_f32x32(p.z + pix * (size_t)p.hid + col, v, 32, true);
+        } else {                                      // r gate -> r*h, re-split for the q convolution
+          const int hc = col - p.hid;
+          const float4* hp = reinterpret_cast<const float4*>(p.h + pix * (size_t)p.hid + hc);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 hv = __ldg(hp + j);
+            v[4 * j] = sigmoidf_acc(v[4 * j]) * hv.x;
+            v[4 * j + 1] = sigmoidf_acc(v[4 * j + 1]) * hv.y;
+            v[4 * j + 2] = sigmoidf_acc(v[4 * j + 2]) * hv.z;
+            v[4 * j + 3] = sigmoidf_acc(v[4 * j + 3]) * hv.w;
+          }
+          const size_t o = pix * (size_t)p.h_stride + p.h_c0 + hc;
+          store_split32(p.out_hi + o, p.out_lo + o, v);
+        }
+      } else {  // EPI_GRU_Q
+        float* hrow = p.h + pix * (size_t)p.hid + col;
+        const float4* hp = reinterpret_cast<const float4*>(hrow);
+        const float4* zp = reinterpret_cast<const float4*>(p.z + pix * (size_t)p.hid + col);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 hv = hp[j];
+          const float4 zv = __ldg(zp + j);
+          v[4 * j] = (1.0f - zv.x) * hv.x + zv.x * tanhf(v[4 * j]);
+          v[4 * j + 1] = (1.0f - zv.y) * hv.y + zv.y * tanhf(v[4 * j + 1]);
+          v[4 * j + 2] = (1.0f - zv.z) * hv.z + zv.z * tanhf(v[4 * j + 2]);
+          v[4 * j + 3] = (1.0f - zv.w) * hv.w + zv.w * tanhf(v[4 * j + 3]);
+        }
+        store_f32x32(hrow, v, 32, true);
+        const size_t o = pix * (size_t)p.h_stride + p.h_c0 + col;
+        store_split32(p.out_hi + o, p.out_lo + o, v);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------
+inline void tc_pick_tile(int W, int H, int* tw, int* th) {
+  // TW*TH = 128 with TW a power of two; minimise padded area, prefer wide tiles on ties.
+  long best = -1;
+  for (int t = 128; t >= 8; t >>= 1) {
+    const int hh = 128 / t;
+    const long area = (long)round_up(W, t) * round_up(H, hh);
+    if (best < 0 || area < best) {
+      best = area;
+      *tw = t;
+      *th = hh;
+    }
+  }
+}
+
+// Fills the derived launch fields (tile grid, stages, TMEM columns) of `p`; returns bytes of
+// dynamic shared memory.  Caller has set bn, B, H, W, TH, TW.
+inline int tc_finalize(TcConvParams& p) {
+  p.tiles_x = ceil_div(p.W, p.TW);
+  p.tiles_y = ceil_div(p.H, p.TH);
+  p.stage_bytes = 2 * kABytes + 2 * p.bn * kChunkK * 2;
+  int nst = kSmemBudget / p.stage_bytes;
+  if (nst > 8) nst = 8;
+  p.nstages = nst;
+  int cols = 32;
+  while (cols < p.bn) cols <<= 1;
+  p.tmem_cols = cols;
+  return nst * p.stage_bytes + 1024 /*align slack*/ + (2 * nst + 1) * 8 + 16;
+}
+
+inline int tc_launch(TcConvParams& p, int n_tiles_n, cudaStream_t stream) {
+  if (p.bn % 16 != 0 || p.bn < 16 || p.bn > 256 || p.TW * p.TH != kTileM) return RAFT_ERR_BAD_SHAPE;
+  const int smem = tc_finalize(p);
+  if (p.nstages < 2) return RAFT_ERR_UNSUPPORTED;
+  static bool attr_set = false;   // benign race: idempotent
+  if (!attr_set) {
+    RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)(p.B * p.tiles_y * p.tiles_x), (unsigned)n_tiles_n, 1);
+  conv_tc_kernel<<<grid, kTcThreads, smem, stream>>>(p);
+  return raft_launch_status();
+}
+
+}  // namespace raft

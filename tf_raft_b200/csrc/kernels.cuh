@@ -1,0 +1,463 @@
+// CUDA-core kernels of the RAFT hot path: pyramid lookup (HBM gather), convex upsampling, the fp32
+// FFMA contraction path (correlation GEMM, generic NHWC convolution), GRU gating, hi/lo splitting,
+// weight re-layout.  All NHWC, fp32 unless a __half plane is named.
+#pragma once
+#include "common.cuh"
+
+namespace raft {
+
+// ------------------------------------------------------------------------------------------------
+// fp32 plane -> fp16 hi/lo planes (operand format of the tensor-core path)
+//   src (npix, src_stride) channels [src_c0, src_c0+nch)  ->  hi/lo (npix, dst_stride) at dst_c0;
+//   channels [nch, nch_pad) of the destination are written as zeros.
+// ------------------------------------------------------------------------------------------------
+__global__ void split_plane_kernel(const float* __restrict__ src, int src_stride, int src_c0, int nch, int nch_pad,
+                                   __half* __restrict__ hi, __half* __restrict__ lo, int dst_stride, int dst_c0,
+                                   size_t npix, float scale) {
+  const size_t total = npix * (size_t)nch_pad;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t px = i / nch_pad;
+    const int c = (int)(i - px * nch_pad);
+    __half h = __float2half_rn(0.f), l = h;
+    if (c < nch) split_f16(src[px * src_stride + src_c0 + c] * scale, h, l);
+    hi[px * dst_stride + dst_c0 + c] = h;
+    lo[px * dst_stride + dst_c0 + c] = l;
+  }
+}
+
+// 2x2 mean, VALID (floors odd dims), over the two spatial dims of (M, H, W, C) -> (M, H/2, W/2, C).
+// Used on the correlation volume (C = 1, corr.py:113) and, by linearity, on fmap2 (C = 256).
+__global__ void avgpool2x2_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t M, int H, int W,
+                                  int C) {
+  const int Ho = H / 2, Wo = W / 2;
+  const size_t total = M * (size_t)Ho * Wo * C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    size_t t = i;
+    const int c = (int)(t % C);
+    t /= C;
+    const int xo = (int)(t % Wo);
+    t /= Wo;
+    const int yo = (int)(t % Ho);
+    const size_t m = t / Ho;
+    const float* s = src + ((m * H + 2 * yo) * W + 2 * xo) * (size_t)C + c;
+    const float a = s[0], b = s[C], cc = s[(size_t)W * C], d = s[(size_t)W * C + C];
+    dst[i] = __fmul_rn(__fadd_rn(__fadd_rn(a, b), __fadd_rn(cc, d)), 0.25f);
+  }
+}
+
+// coords_grid (corr.py:72-90)
+__global__ void coords_grid_kernel(float* __restrict__ out, int B, int h, int w) {
+  const size_t total = (size_t)B * h * w;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % w), y = (int)((i / w) % h);
+    out[2 * i] = (float)x;
+    out[2 * i + 1] = (float)y;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// bilinear_sampler (corr.py:28-69), one sample.  floor/ceil corners: an integer (or clamped)
+// coordinate gives zero weight on all four corners.  Every operation is individually rounded
+// (__f*_rn) so the result is bit-identical to the op-by-op NumPy/TF evaluation.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sample_floor_ceil(const float* __restrict__ img, int H, int W, float px, float py) {
+  const float gx = fminf(fmaxf(px, 0.0f), (float)(W - 1));
+  const float gy = fminf(fmaxf(py, 0.0f), (float)(H - 1));
+  const float gx0 = floorf(gx), gx1 = ceilf(gx), gy0 = floorf(gy), gy1 = ceilf(gy);
+  const float wy1 = __fsub_rn(gy1, gy), wy0 = __fsub_rn(gy, gy0);
+  const float wx1 = __fsub_rn(gx1, gx), wx0 = __fsub_rn(gx, gx0);
+  const float c00 = __fmul_rn(wy1, wx1), c01 = __fmul_rn(wy1, wx0);
+  const float c10 = __fmul_rn(wy0, wx1), c11 = __fmul_rn(wy0, wx0);
+  const int ix0 = (int)gx0, ix1 = (int)gx1, iy0 = (int)gy0, iy1 = (int)gy1;
+  const float x00 = __ldg(img + iy0 * W + ix0), x01 = __ldg(img + iy0 * W + ix1);
+  const float x10 = __ldg(img + iy1 * W + ix0), x11 = __ldg(img + iy1 * W + ix1);
+  float acc = __fmul_rn(c00, x00);
+  acc = __fadd_rn(acc, __fmul_rn(c01, x01));
+  acc = __fadd_rn(acc, __fmul_rn(c10, x10));
+  acc = __fadd_rn(acc, __fmul_rn(c11, x11));
+  return acc;
+}
+
+__global__ void bilinear_sampler_kernel(const float* __restrict__ image, const float* __restrict__ coords, int M, int H,
+                                        int W, int P, float* __restrict__ out) {
+  const size_t total = (size_t)M * P;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t m = i / P;
+    out[i] = sample_floor_ceil(image + m * (size_t)H * W, H, W, coords[2 * i], coords[2 * i + 1]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CorrBlock.retrieve (corr.py:116-152).  One warp per (query pixel, level); lanes stride over the
+// (2r+1)^2 taps, so the output row segment is written coalesced.  Tap t = a*(2r+1)+b has x-offset
+// a-r and y-offset b-r (corr.py:133-143).  Optionally also emits the fp16 hi/lo planes the
+// tensor-core update block consumes (channels beyond levels*(2r+1)^2 up to h_pad are zeroed).
+// ------------------------------------------------------------------------------------------------
+struct LookupParams {
+  const float* pyr[RAFT_MAX_LEVELS];
+  int lh[RAFT_MAX_LEVELS], lw[RAFT_MAX_LEVELS];
+  const float* coords;
+  float* out; int out_stride;
+  __half* out_hi; __half* out_lo; int h_stride, h_pad;
+  int nq;      // B*h*w
+  int levels, radius;
+};
+
+__global__ void __launch_bounds__(256) corr_lookup_kernel(const LookupParams p) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int side = 2 * p.radius + 1, ntap = side * side;
+  const size_t nwork = (size_t)p.nq * p.levels;
+  for (size_t wi = (size_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); wi < nwork;
+       wi += (size_t)gridDim.x * warps_per_block) {
+    const int q = (int)(wi / p.levels), l = (int)(wi % p.levels);
+    const int H = p.lh[l], W = p.lw[l];
+    const float* img = p.pyr[l] + (size_t)q * H * W;
+    const float inv = 1.0f / (float)(1 << l);                    // exact power of two
+    const float cx = __fmul_rn(__ldg(p.coords + 2 * (size_t)q), inv);     // coords / 2**i  (corr.py:141)
+    const float cy = __fmul_rn(__ldg(p.coords + 2 * (size_t)q + 1), inv);
+    for (int t = lane; t < ntap; t += 32) {
+      const int a = t / side, b2 = t - a * side;
+      const float px = __fadd_rn(cx, (float)(a - p.radius));     // centroid + delta (corr.py:143)
+      const float py = __fadd_rn(cy, (float)(b2 - p.radius));
+      const float v = sample_floor_ceil(img, H, W, px, py);
+      const int ch = l * ntap + t;
+      if (p.out) p.out[(size_t)q * p.out_stride + ch] = v;
+      if (p.out_hi) {
+        __half hh, ll;
+        split_f16(v, hh, ll);
+        p.out_hi[(size_t)q * p.h_stride + ch] = hh;
+        p.out_lo[(size_t)q * p.h_stride + ch] = ll;
+      }
+    }
+    if (p.out_hi && l == p.levels - 1) {
+      const __half zero = __float2half_rn(0.f);
+      for (int c = p.levels * ntap + lane; c < p.h_pad; c += 32) {
+        p.out_hi[(size_t)q * p.h_stride + c] = zero;
+        p.out_lo[(size_t)q * p.h_stride + c] = zero;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 correlation (RAFT_PREC_FP32): out[b, q, n] = <f1[b,q,:], f2[b,n,:]> / sqrt(C)  (corr.py:154-162)
+// 64x64 tile, 16-wide K slab, 4x4 micro-tile per thread.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) corr_fp32_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
+                                                        float* __restrict__ out, int N, int C, float div) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Bs[16][64 + 4];
+  const int b = blockIdx.z;
+  const float* A = f1 + (size_t)b * N * C;
+  const float* Bm = f2 + (size_t)b * N * C;
+  float* O = out + (size_t)b * N * N;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int lr = threadIdx.x >> 2, lc = (threadIdx.x & 3) * 4;   // loader: row 0..63, 4 consecutive k
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < C; k0 += 16) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + lc + j;
+      As[lc + j][lr] = (m0 + lr < N && k < C) ? A[(size_t)(m0 + lr) * C + k] : 0.f;
+      Bs[lc + j][lr] = (n0 + lr < N && k < C) ? Bm[(size_t)(n0 + lr) * C + k] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float a[4], w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        a[i] = As[k][ty * 4 + i];
+        w[i] = Bs[k][tx * 4 + i];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int m = m0 + ty * 4 + i, n = n0 + tx * 4 + j;
+      if (m < N && n < N) O[(size_t)m * N + n] = __fdiv_rn(acc[i][j], div);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Generic stride-1 'same' convolution, fp32 FFMA (RAFT_PREC_FP32 path and the Cin=2 7x7 flow conv
+// of the tensor-core path).  Input = channel concat of up to 3 NHWC sources; HWIO weights.
+//   out[pix, c0+n] = act(bias[n] + sum_{tap,c} in[pix+tap, c] * w[tap, c, n]) * out_scale
+// 64 px x 64 cout tile, 16-channel slab per tap, 4x4 micro-tile per thread.
+// ------------------------------------------------------------------------------------------------
+enum SimtAct : int { SACT_NONE = 0, SACT_RELU = 1, SACT_SIGMOID = 2, SACT_TANH = 3 };
+
+struct SimtConvParams {
+  const float* src[3]; int src_stride[3], src_c0[3], src_n[3]; int nsrc;
+  const float* w; const float* bias;         // HWIO (kh, kw, cin, cout)
+  int kh, kw, cin, cout;
+  int B, H, W;
+  float* out; int out_stride, out_c0;
+  __half* out_hi; __half* out_lo; int h_stride, h_c0;   // optional fp16 hi/lo copy of the output
+  int act; float out_scale;
+};
+
+__global__ void __launch_bounds__(256) conv_simt_kernel(const SimtConvParams p) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Ws[16][64 + 4];
+  const int npix = p.B * p.H * p.W;
+  const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int lr = threadIdx.x >> 2, lc = (threadIdx.x & 3) * 4;   // A loader: pixel row, 4 channels
+  const int wr = threadIdx.x >> 4, wc = (threadIdx.x & 15) * 4;  // W loader: k row, 4 couts
+  const int ph = (p.kh - 1) / 2, pw = (p.kw - 1) / 2;
+  // this thread's loader pixel
+  const int lp = m0 + lr;
+  int lb = 0, ly = 0, lx = 0;
+  if (lp < npix) {
+    lx = lp % p.W;
+    ly = (lp / p.W) % p.H;
+    lb = lp / (p.W * p.H);
+  }
+  float acc[4][4] = {};
+  for (int tap = 0; tap < p.kh * p.kw; ++tap) {
+    const int dy = tap / p.kw - ph, dx = tap % p.kw - pw;
+    const int sy = ly + dy, sx = lx + dx;
+    const bool inb = lp < npix && sy >= 0 && sy < p.H && sx >= 0 && sx < p.W;
+    const size_t spix = ((size_t)lb * p.H + (inb ? sy : 0)) * p.W + (inb ? sx : 0);
+    for (int k0 = 0; k0 < p.cin; k0 += 16) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = k0 + lc + j;
+        float v = 0.f;
+        if (inb && c < p.cin) {
+          int cc = c, s = 0;
+          while (s < p.nsrc - 1 && cc >= p.src_n[s]) cc -= p.src_n[s++];
+          v = __ldg(p.src[s] + spix * p.src_stride[s] + p.src_c0[s] + cc);
+        }
+        As[lc + j][lr] = v;
+      }
+      {
+        const int c = k0 + wr;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int n = n0 + wc + j;
+          Ws[wr][wc + j] = (c < p.cin && n < p.cout) ? __ldg(p.w + ((size_t)tap * p.cin + c) * p.cout + n) : 0.f;
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        float a[4], w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          a[i] = As[k][ty * 4 + i];
+          w[i] = Ws[k][tx * 4 + i];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= npix) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= p.cout) continue;
+      float v = acc[i][j] + (p.bias ? __ldg(p.bias + n) : 0.f);
+      if (p.act == SACT_RELU) v = fmaxf(v, 0.f);
+      else if (p.act == SACT_SIGMOID) v = sigmoidf_acc(v);
+      else if (p.act == SACT_TANH) v = tanhf(v);
+      v *= p.out_scale;
+      if (p.out) p.out[(size_t)m * p.out_stride + p.out_c0 + n] = v;
+      if (p.out_hi) {
+        __half hh, ll;
+        split_f16(v, hh, ll);
+        p.out_hi[(size_t)m * p.h_stride + p.h_c0 + n] = hh;
+        p.out_lo[(size_t)m * p.h_stride + p.h_c0 + n] = ll;
+      }
+    }
+  }
+}
+
+// GRU gating (update.py:32-34, 55-66), fp32 path.
+__global__ void gru_rh_kernel(const float* __restrict__ r, const float* __restrict__ h, float* __restrict__ rh,
+                              size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    rh[i] = r[i] * h[i];
+}
+__global__ void gru_update_kernel(const float* __restrict__ z, const float* __restrict__ q, float* __restrict__ h,
+                                  size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    h[i] = (1.0f - z[i]) * h[i] + z[i] * q[i];
+}
+
+// Strided channel copy: dst[px, dst_c0 + c] = src[px, src_c0 + c], c < n.
+__global__ void copy_channels_kernel(const float* __restrict__ src, int src_stride, int src_c0,
+                                     float* __restrict__ dst, int dst_stride, int dst_c0, int n, size_t npix) {
+  const size_t total = npix * (size_t)n;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t px = i / n;
+    const int c = (int)(i - px * n);
+    dst[px * dst_stride + dst_c0 + c] = src[px * src_stride + src_c0 + c];
+  }
+}
+
+// model.py:97,102: coords1 += delta_flow (in place); flow = coords1 - coords0 with coords0 the
+// pixel grid (model.py:89), recomputed from the index instead of being stored.
+__global__ void flow_advance_kernel(float* __restrict__ coords1, const float* __restrict__ delta,
+                                    float* __restrict__ flow, int B, int h, int w) {
+  const size_t total = (size_t)B * h * w;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const float gx = (float)(i % w), gy = (float)((i / w) % h);
+    float cx = coords1[2 * i], cy = coords1[2 * i + 1];
+    if (delta) {
+      cx = __fadd_rn(cx, delta[2 * i]);
+      cy = __fadd_rn(cy, delta[2 * i + 1]);
+      coords1[2 * i] = cx;
+      coords1[2 * i + 1] = cy;
+    }
+    flow[2 * i] = __fsub_rn(cx, gx);
+    flow[2 * i + 1] = __fsub_rn(cy, gy);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// RAFT.upsample_flow (model.py:39-66): one 64-thread group per coarse pixel, thread = (by, bx).
+// mask channel (by*8+bx)*9 + ky*3+kx; softmax over the 9 taps; neighbours of 8*flow zero-padded.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) upsample_convex_kernel(const float* __restrict__ flow,
+                                                              const float* __restrict__ mask, int B, int h, int w,
+                                                              float* __restrict__ out) {
+  const int sub = threadIdx.x & 63;
+  const size_t npix = (size_t)B * h * w;
+  for (size_t pix = (size_t)blockIdx.x * 4 + (threadIdx.x >> 6); pix < npix; pix += (size_t)gridDim.x * 4) {
+    const int x = (int)(pix % w), y = (int)((pix / w) % h), b = (int)(pix / ((size_t)w * h));
+    const float* mp = mask + pix * 576 + sub * 9;
+    float m[9], mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      m[k] = __ldg(mp + k);
+      mx = fmaxf(mx, m[k]);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      m[k] = expf(m[k] - mx);
+      sum += m[k];
+    }
+    float ox = 0.f, oy = 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const int yy = y + k / 3 - 1, xx = x + k % 3 - 1;
+      float fx = 0.f, fy = 0.f;
+      if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
+        const float* fp = flow + (((size_t)b * h + yy) * w + xx) * 2;
+        fx = 8.0f * __ldg(fp);
+        fy = 8.0f * __ldg(fp + 1);
+      }
+      const float wk = m[k] / sum;
+      ox += wk * fx;
+      oy += wk * fy;
+    }
+    const int by = sub >> 3, bx = sub & 7;
+    float* op = out + ((((size_t)b * 8 * h) + 8 * y + by) * (8 * (size_t)w) + 8 * x + bx) * 2;
+    *reinterpret_cast<float2*>(op) = make_float2(ox, oy);
+  }
+}
+
+// upflow8 (corr.py:93-96): 8 * bilinear resize, half-pixel centres, edge-clamped source indices.
+__global__ void upflow8_kernel(const float* __restrict__ flow, int B, int h, int w, float* __restrict__ out) {
+  const int H = 8 * h, W = 8 * w;
+  const size_t total = (size_t)B * H * W;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int X = (int)(i % W), Y = (int)((i / W) % H), b = (int)(i / ((size_t)W * H));
+    const float sx = ((float)X + 0.5f) * 0.125f - 0.5f, sy = ((float)Y + 0.5f) * 0.125f - 0.5f;
+    const float fx0 = floorf(sx), fy0 = floorf(sy);
+    const float ax = sx - fx0, ay = sy - fy0;
+    const int x0 = min(max((int)fx0, 0), w - 1), x1 = min(max((int)fx0 + 1, 0), w - 1);
+    const int y0 = min(max((int)fy0, 0), h - 1), y1 = min(max((int)fy0 + 1, 0), h - 1);
+    const float* f = flow + (size_t)b * h * w * 2;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const float v00 = f[((size_t)y0 * w + x0) * 2 + c], v01 = f[((size_t)y0 * w + x1) * 2 + c];
+      const float v10 = f[((size_t)y1 * w + x0) * 2 + c], v11 = f[((size_t)y1 * w + x1) * 2 + c];
+      const float top = v00 * (1.f - ax) + v01 * ax, bot = v10 * (1.f - ax) + v11 * ax;
+      out[2 * i + c] = 8.0f * (top * (1.f - ay) + bot * ay);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight re-layout for the tensor-core path.
+//   HWIO fp32 (kh,kw,cin,cout)  ->  [tap][cout_pad][cin_pad] fp16 hi / lo planes of w * 2^k,
+//   placed at (cout_off, cin remapped through up to two ranges).  2^k is chosen so that
+//   max|w|*2^k lies in [2^12, 2^13): the lo residuals then stay in fp16's normal range.
+// ------------------------------------------------------------------------------------------------
+__global__ void absmax_kernel(const float* __restrict__ w, size_t n, unsigned int* __restrict__ out_bits) {
+  float m = 0.f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(w[i]));
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));   // non-negative floats order as uints
+}
+
+// scale[0] = 2^k, scale[1] = 2^-k from the absmax bits (shared by all convs merged into one layer)
+__global__ void weight_scale_kernel(const unsigned int* __restrict__ absmax_bits, float* __restrict__ scale) {
+  const float m = __uint_as_float(*absmax_bits);
+  int k = 0;
+  if (m > 0.f && isfinite(m)) {
+    int e;
+    frexpf(m, &e);          // m = f * 2^e, f in [0.5, 1)  ->  m*2^(13-e) in [2^12, 2^13)
+    k = 13 - e;
+    k = max(-24, min(24, k));
+  }
+  scale[0] = ldexpf(1.0f, k);
+  scale[1] = ldexpf(1.0f, -k);
+}
+
+struct PackParams {
+  const float* w; int kh, kw, cin, cout;
+  __half* hi; __half* lo; int cout_pad, cin_pad, cout_off;
+  int r_src0[2], r_n[2], r_dst0[2], nrange;     // cin remap ranges
+  const float* scale;                           // scale[0] = 2^k
+};
+__global__ void pack_weights_kernel(const PackParams p) {
+  const size_t total = (size_t)p.kh * p.kw * p.cin * p.cout;
+  const float s = p.scale[0];
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    size_t t = i;
+    const int n = (int)(t % p.cout);
+    t /= p.cout;
+    const int c = (int)(t % p.cin);
+    const int tap = (int)(t / p.cin);
+    int cd = -1;
+    for (int r = 0; r < p.nrange; ++r)
+      if (c >= p.r_src0[r] && c < p.r_src0[r] + p.r_n[r]) cd = p.r_dst0[r] + (c - p.r_src0[r]);
+    if (cd < 0) continue;
+    __half hh, ll;
+    split_f16(p.w[i] * s, hh, ll);
+    const size_t o = ((size_t)tap * p.cout_pad + p.cout_off + n) * p.cin_pad + cd;
+    p.hi[o] = hh;
+    p.lo[o] = ll;
+  }
+}
+
+inline int grid_for(size_t n, int block = 256, int cap = kNumSMs * 16) {
+  size_t g = (n + block - 1) / block;
+  if (g < 1) g = 1;
+  if (g > (size_t)cap) g = cap;
+  return (int)g;
+}
+
+}  // namespace raft

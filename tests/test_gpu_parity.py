@@ -1,0 +1,226 @@
+"""Parity of the CUDA path against the CPU oracle, through the C ABI (via the Python mirror).
+
+Every test runs both arithmetic paths: 'f16x2' (tcgen05 tensor cores, the product path) and 'fp32'
+(CUDA-core FFMA).  Index / gather work is compared bit for bit; contractions within stated fp32
+tolerances; the final flow within BASELINE.json's 1e-3 max-abs gate.
+"""
+import numpy as np
+import pytest
+import torch
+
+import cases
+from oracle import corr_np, raft_torch as rt, weights
+
+pytestmark = pytest.mark.gpu
+PRECISIONS = ('f16x2', 'fp32')
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.fixture(scope='module')
+def T():
+    import tf_raft_b200
+    from tf_raft_b200 import _lib
+    assert _lib.lib().raft_b200_device_ok(torch.cuda.current_device()) == 0, 'needs an sm_100 GPU'
+    return tf_raft_b200
+
+
+# --------------------------------------------------------------------------------------------- CorrBlock
+@pytest.mark.parametrize('precision', PRECISIONS)
+@pytest.mark.parametrize('tag,shape', [('a', (2, 8, 12, 64, 4, 4)), ('b', (1, 9, 7, 128, 3, 3))])
+def test_corr_pyramid_vs_golden(T, golden, precision, tag, shape):
+    b, h, w, c, r, levels = shape
+    f1, f2 = cases.fmaps(b, h, w, c)
+    cb = T.CorrBlock(dev(f1), dev(f2), num_levels=levels, radius=r, precision=precision)
+    assert len(cb.corr_pyramid) == levels
+    for l, p in enumerate(cb.corr_pyramid):
+        want = golden['corr_lookup'][f'{tag}_pyr{l}']
+        assert tuple(p.shape) == want.shape
+        np.testing.assert_allclose(p.cpu().numpy(), want, atol=2e-5, rtol=2e-5, err_msg=f'level {l}')
+
+
+@pytest.mark.parametrize('tag,shape', [('a', (2, 8, 12, 64, 4, 4)), ('b', (1, 9, 7, 128, 3, 3))])
+@pytest.mark.parametrize('kind', ['grid', 'jitter', 'edge'])
+def test_lookup_bit_exact_given_the_oracle_pyramid(T, golden, tag, shape, kind):
+    """Gather + bilinear weights are index/elementwise work: bit-identical to the op-by-op oracle, including
+    integer => 0, clamp => 0 and the x-major tap order (SURVEY.md traps 1-4)."""
+    b, h, w, c, r, levels = shape
+    f1, f2 = cases.fmaps(b, h, w, c)
+    cb = T.CorrBlock(dev(f1), dev(f2), num_levels=levels, radius=r, precision='fp32')
+    cb.corr_pyramid = [dev(golden['corr_lookup'][f'{tag}_pyr{l}']) for l in range(levels)]
+    out = cb.retrieve(dev(cases.lookup_coords(b, h, w, kind))).cpu().numpy()
+    np.testing.assert_array_equal(out, golden['corr_lookup'][f'{tag}_lookup_{kind}'])
+
+
+def test_bilinear_sampler_reference_test_and_quirks(T):
+    """reference tests/layers/test_corr.py:15-27 on the CUDA sampler, then bit-exactness incl. quirks."""
+    rng = np.random.default_rng(1)
+    m, h, w, r = 512, 32, 32, 4
+    image = rng.standard_normal((m, h, w, 1)).astype(np.float32)
+    coords = np.stack([rng.uniform(0, w - 1, (m, 9, 9)), rng.uniform(0, h - 1, (m, 9, 9))], axis=-1).astype(np.float32)
+    got = T.bilinear_sampler(dev(image), dev(coords)).cpu().numpy()
+    np.testing.assert_allclose(got, corr_np.standard_bilinear(image, coords), atol=1e-5, rtol=1e-5)
+    np.testing.assert_array_equal(got, corr_np.bilinear_sampler(image, coords))
+    coords[::3] = np.round(coords[::3])
+    coords[1::5] += 40
+    np.testing.assert_array_equal(T.bilinear_sampler(dev(image), dev(coords)).cpu().numpy(),
+                                  corr_np.bilinear_sampler(image, coords))
+
+
+def test_coords_grid_and_upflow8(T):
+    np.testing.assert_array_equal(T.coords_grid(2, 5, 7).cpu().numpy(), corr_np.coords_grid(2, 5, 7))
+    flow = np.random.default_rng(4).standard_normal((2, 6, 9, 2)).astype(np.float32)
+    np.testing.assert_allclose(T.upflow8(dev(flow)).cpu().numpy(), corr_np.upflow8(flow), atol=1e-5, rtol=1e-5)
+
+
+def test_corr_block_correlation_method(T):
+    f1, f2 = cases.fmaps(1, 8, 8, 64)
+    cb = T.CorrBlock(dev(f1), dev(f2), 2, 3)
+    vol = cb.correlation(dev(f1), dev(f2))
+    assert tuple(vol.shape) == (1, 8, 8, 1, 8, 8)
+    np.testing.assert_allclose(vol.cpu().numpy(), corr_np.CorrBlock.correlation(f1, f2), atol=2e-5, rtol=2e-5)
+
+
+# --------------------------------------------------------------------------------------------- update blocks
+@pytest.mark.parametrize('precision', PRECISIONS)
+@pytest.mark.parametrize('variant', ['raft', 'small'])
+def test_update_block_vs_golden(T, golden, precision, variant):
+    p = weights.init_params(variant, 1234, bias_scale=0.05)
+    blk = (T.BasicUpdateBlock if variant == 'raft' else T.SmallUpdateBlock)(precision=precision)
+    blk.load_params(p, 'update_block.')
+    net, inp, corr, flow = cases.update_inputs(variant, 1, 8, 8)
+    n2, mask, delta = blk([dev(net), dev(inp), dev(corr), dev(flow)])
+    g = golden['update_blocks']
+    np.testing.assert_allclose(n2.cpu().numpy(), g[f'{variant}_net'], atol=2e-5, rtol=1e-4)
+    np.testing.assert_allclose(delta.cpu().numpy(), g[f'{variant}_delta'], atol=5e-5, rtol=1e-4)
+    if variant == 'raft':
+        np.testing.assert_allclose(mask.cpu().numpy(), g['raft_mask'], atol=5e-5, rtol=1e-4)
+    else:
+        assert mask is None
+
+
+@pytest.mark.parametrize('precision', PRECISIONS)
+def test_update_block_ragged_grid(T, precision):
+    """A grid that is not a multiple of the 128-pixel tile in either direction (13 x 11), batch 3."""
+    p = weights.init_params('raft', 7, bias_scale=0.05)
+    blk = T.BasicUpdateBlock(precision=precision)
+    blk.load_params(p, 'update_block.')
+    net, inp, corr, flow = cases.update_inputs('raft', 3, 13, 11, seed=21)
+    n2, mask, delta = blk([dev(net), dev(inp), dev(corr), dev(flow)])
+    ops = rt.Ops(p)
+    t = [torch.from_numpy(a).permute(0, 3, 1, 2) for a in (net, inp, corr, flow)]
+    on, om, od = rt.basic_update_block(ops, *t)
+    np.testing.assert_allclose(n2.cpu().numpy(), on.permute(0, 2, 3, 1).numpy(), atol=2e-5, rtol=1e-4)
+    np.testing.assert_allclose(delta.cpu().numpy(), od.permute(0, 2, 3, 1).numpy(), atol=5e-5, rtol=1e-4)
+    np.testing.assert_allclose(mask.cpu().numpy(), om.permute(0, 2, 3, 1).numpy(), atol=5e-5, rtol=1e-4)
+
+
+def test_upsample_convex_vs_oracle(T):
+    rng = np.random.default_rng(3)
+    flow = rng.standard_normal((2, 5, 6, 2)).astype(np.float32) * 3
+    mask = rng.standard_normal((2, 5, 6, 576)).astype(np.float32)
+    model = T.RAFT(iters=1, iters_pred=1)
+    got = model.upsample_flow(dev(flow), dev(mask)).cpu().numpy()
+    want = rt.upsample_flow(torch.from_numpy(flow), torch.from_numpy(mask)).numpy()
+    np.testing.assert_allclose(got, want, atol=1e-5, rtol=1e-5)
+    # convexity: a constant flow field upsamples to 8x that constant away from the zero-padded border
+    const = np.ones((1, 5, 6, 2), np.float32) * np.array([1.5, -2.0], np.float32)
+    up = model.upsample_flow(dev(const), dev(mask[:1])).cpu().numpy()
+    np.testing.assert_allclose(up[:, 8:-8, 8:-8], np.broadcast_to(8 * const[0, 0, 0], up[:, 8:-8, 8:-8].shape), rtol=1e-5)
+
+
+# --------------------------------------------------------------------------------------------- models
+def _run_model(T, variant, precision, params, im1, im2, iters):
+    cls = T.RAFT if variant == 'raft' else T.SmallRAFT
+    model = cls(drop_rate=0, iters=iters, iters_pred=iters, precision=precision)
+    model.load_params(params)
+    return model([dev(im1), dev(im2)], training=False)
+
+
+@pytest.mark.parametrize('precision', PRECISIONS)
+def test_small_raft_config1_vs_golden(T, golden, precision):
+    """BASELINE.json configs[0]: SmallRAFT, 1 pair 64x128, iters=3."""
+    p = weights.init_params('small', 1234, bias_scale=0.05, norm_jitter=0.1)
+    im1, im2 = cases.images(1, 64, 128)
+    preds = _run_model(T, 'small', precision, p, im1, im2, 3)
+    assert len(preds) == 3 and all(tuple(q.shape) == (1, 64, 128, 2) for q in preds)
+    want = golden['models']['small_64x128_it3']
+    for i, q in enumerate(preds):
+        err = np.abs(q.cpu().numpy() - want[i]).max()
+        assert err <= 1e-3, f'iteration {i}: max-abs {err}'
+
+
+@pytest.mark.parametrize('precision', PRECISIONS)
+def test_raft_reference_test_shape_vs_golden(T, golden, precision):
+    """RAFT at the reference test's 64x96 (tests/test_model.py:10-11), 4 iterations; gate 1e-3 max-abs."""
+    p = weights.init_params('raft', 1234, bias_scale=0.05, norm_jitter=0.1)
+    im1, im2 = cases.images(1, 64, 96)
+    preds = _run_model(T, 'raft', precision, p, im1, im2, 4)
+    want = golden['models']['raft_64x96_it4']
+    assert len(preds) == 4
+    for i, q in enumerate(preds):
+        err = np.abs(q.cpu().numpy() - want[i]).max()
+        assert err <= 1e-3, f'iteration {i}: max-abs {err}'
+
+
+def test_model_api_contract(T):
+    """reference tests/test_model.py:44-77: training -> iters outputs, inference -> iters_pred outputs, each
+    (B, H, W, 2); the B=4, 64x96 shape of the reference test."""
+    im1, im2 = cases.images(4, 64, 96)
+    for cls in (T.RAFT, T.SmallRAFT):
+        model = cls(drop_rate=0.0, iters=2, iters_pred=3)
+        out = model([dev(im1), dev(im2)], training=True)
+        assert len(out) == 2 and all(tuple(f.shape) == (4, 64, 96, 2) for f in out)
+        out = model([dev(im1), dev(im2)], training=False)
+        assert len(out) == 3 and all(tuple(f.shape) == (4, 64, 96, 2) for f in out)
+        assert tuple(model.predict_step((dev(im1), dev(im2))).shape) == (4, 64, 96, 2)
+        assert torch.isfinite(out[-1]).all()
+    with pytest.raises(ValueError):
+        T.RAFT()([dev(im1[:, :60]), dev(im2[:, :60])], training=False)      # 60 is not a multiple of 8 (trap 7)
+
+
+# --------------------------------------------------------------------------------------------- full size
+@pytest.fixture(scope='module')
+def full_size_oracle():
+    """BASELINE.json configs[1] shape (448x512, 12 iterations), one pair (the batch axis is independent)."""
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    p = weights.init_params('raft', 1234)
+    im1, im2 = cases.images(1, 448, 512)
+    preds, inter = rt.forward(p, im1, im2, 'raft', 12, return_intermediates=True)
+    return p, im1, im2, preds, inter
+
+
+@pytest.mark.parametrize('precision', PRECISIONS)
+def test_raft_448x512_final_flow(T, full_size_oracle, precision):
+    p, im1, im2, preds, _ = full_size_oracle
+    got = _run_model(T, 'raft', precision, p, im1, im2, 12)
+    err = (got[-1].cpu() - preds[-1]).abs()
+    mag = preds[-1].abs().max().item()
+    msg = (f'final-flow max-abs {err.max().item():.3e} (flow magnitude up to {mag:.1f} px), '
+           f'99.9th pct {err.flatten().kthvalue(int(0.999 * err.numel())).values.item():.3e}')
+    print(precision, msg)
+    assert err.max().item() <= 1e-3, msg
+
+
+@pytest.mark.parametrize('precision', PRECISIONS)
+def test_corr_pyramid_full_size_properties(T, precision):
+    """Size-independent checks at the 56x64 grid of config 2: transpose symmetry, pooling consistency."""
+    f1, f2 = cases.fmaps(1, 56, 64, 256, seed=11)
+    a = T.CorrBlock(dev(f1), dev(f2), 4, 4, precision=precision)
+    b = T.CorrBlock(dev(f2), dev(f1), 1, 4, precision=precision)
+    n = 56 * 64
+    v = a.corr_pyramid[0].reshape(n, n)
+    np.testing.assert_allclose(v.cpu().numpy(), b.corr_pyramid[0].reshape(n, n).t().cpu().numpy(), atol=2e-5, rtol=2e-5)
+    # a few rows against a direct fp64 dot product
+    rows = [0, 1, 777, n - 1]
+    want = (f1.reshape(n, 256)[rows].astype(np.float64) @ f2.reshape(n, 256).T.astype(np.float64)) / 16.0
+    np.testing.assert_allclose(v[rows].cpu().numpy(), want, atol=3e-5, rtol=2e-5)
+    for l in range(1, 4):
+        prev = a.corr_pyramid[l - 1]
+        pooled = torch.nn.functional.avg_pool2d(prev.permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1)
+        np.testing.assert_allclose(a.corr_pyramid[l].cpu().numpy(), pooled.cpu().numpy(), atol=2e-5, rtol=2e-5)
+    # iteration-0 lookup: level 0 is all zeros, the rest is not
+    out = a.retrieve(T.coords_grid(1, 56, 64))
+    assert torch.all(out[..., :81] == 0) and out[..., 81:].abs().max() > 0

@@ -1,0 +1,3 @@
+from .corr import CorrBlock, bilinear_sampler, coords_grid, tfa_sampler, upflow8
+from .extractor import BasicEncoder, SmallEncoder
+from .update import BasicUpdateBlock, SmallUpdateBlock

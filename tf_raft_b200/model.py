@@ -1,0 +1,189 @@
+"""RAFT / SmallRAFT -- host-side mirror of tf_raft/model.py.
+
+`RAFT(drop_rate=0, iters=12, iters_pred=24)([image1, image2], training)` returns the list of
+`iters` (training) or `iters_pred` (inference) flow predictions (B, H, W, 2), like the reference
+(model.py:68-109 / 190-226).  The whole iteration loop (lookup -> update block -> coords += delta ->
+upsample) is ONE call into libraft_b200.so (raft_b200_forward_loop); the correlation pyramid is
+another (raft_b200_corr_pyramid_build).  Optionally the loop is replayed from a CUDA graph.
+"""
+import ctypes
+from collections import OrderedDict
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from .layers.corr import CorrBlock, coords_grid, upflow8
+from .layers.extractor import BasicEncoder, SmallEncoder
+from .layers.update import BasicUpdateBlock, SmallUpdateBlock
+from .losses import end_point_error, sequence_loss
+
+
+class RAFT:
+    _variant = _lib.VARIANT_BASIC
+
+    def __init__(self, drop_rate=0, iters=12, iters_pred=24, *, precision=None, device='cuda', seed=None,
+                 use_graph=False, **kwargs):
+        self.hidden_dim = 128
+        self.context_dim = 128
+        self.corr_levels = 4
+        self.corr_radius = 4
+        self.drop_rate = drop_rate
+        self.iters = iters
+        self.iters_pred = iters_pred
+        self.precision = _lib.resolve_precision(precision)
+        self.device = torch.device(device)
+        self.use_graph = use_graph
+        self._build_layers(seed)
+        self._graphs = {}
+        self.flow_metrics = None
+
+    def _build_layers(self, seed):
+        s = 0 if seed is None else seed
+        self.fnet = BasicEncoder(output_dim=256, norm_type='instance', drop_rate=self.drop_rate, device=self.device,
+                                 seed=s)
+        self.cnet = BasicEncoder(output_dim=self.hidden_dim + self.context_dim, norm_type='batch',
+                                 drop_rate=self.drop_rate, device=self.device, seed=s + 1)
+        self.update_block = BasicUpdateBlock(filters=self.hidden_dim, precision=self.precision, device=self.device,
+                                             seed=s + 2)
+
+    # -- parameters ---------------------------------------------------------------------------
+    def load_params(self, params):
+        """`{'fnet.conv1.kernel': ..., 'cnet....', 'update_block.encoder.convc1.kernel': ...}` (NumPy or torch)."""
+        self.fnet.load_params(params, 'fnet.')
+        self.cnet.load_params(params, 'cnet.')
+        self.update_block.load_params(params, 'update_block.')
+        self._graphs.clear()
+
+    def state_dict(self):
+        out = OrderedDict()
+        out.update(self.fnet.state_dict('fnet.'))
+        out.update(self.cnet.state_dict('cnet.'))
+        out.update(self.update_block.state_dict('update_block.'))
+        return out
+
+    # -- reference helpers ----------------------------------------------------------------------
+    def initialize_flow(self, image):
+        """model.py:32-37: coords0 = coords1 = coords_grid(B, H//8, W//8)."""
+        bs, h, w, _ = image.shape
+        return coords_grid(bs, h // 8, w // 8, self.device), coords_grid(bs, h // 8, w // 8, self.device)
+
+    def upsample_flow(self, flow, mask):
+        """model.py:39-66: convex 8x upsampling."""
+        flow, mask = _lib.f32c(flow), _lib.f32c(mask)
+        b, h, w, _ = flow.shape
+        if tuple(mask.shape) != (b, h, w, 576):
+            raise ValueError(f'mask: expected {(b, h, w, 576)}, got {tuple(mask.shape)}')
+        out = torch.empty((b, 8 * h, 8 * w, 2), dtype=torch.float32, device=flow.device)
+        with torch.cuda.device(flow.device):
+            _lib.check(_lib.lib().raft_b200_upsample_convex(_lib.ptr(flow), _lib.ptr(mask), b, h, w, _lib.ptr(out),
+                                                            _lib.stream()), 'upsample_convex')
+        return out
+
+    # -- forward ----------------------------------------------------------------------------------
+    def _encode(self, image1, image2, training):
+        image1 = 2 * (image1 / 255.0) - 1.0                                   # model.py:70-71
+        image2 = 2 * (image2 / 255.0) - 1.0
+        fmap1, fmap2 = self.fnet([image1, image2], training=training)         # :74
+        cnet = self.cnet(image1, training=training)                           # :82
+        net = torch.tanh(cnet[..., :self.hidden_dim]).contiguous()            # :84-86
+        inp = F.relu(cnet[..., self.hidden_dim:]).contiguous()
+        return fmap1, fmap2, net, inp
+
+    def _loop(self, corr_block, net, inp, coords1, flow_ups, b, h, w):
+        ub = self.update_block
+        ws = ub.workspace(b, h, w)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().raft_b200_forward_loop(
+                self._variant, _lib.ptr(ub.prepared()), _lib.ptr_array(corr_block.corr_pyramid), self.corr_levels,
+                self.corr_radius, _lib.ptr(net), _lib.ptr(inp), _lib.ptr(coords1), _lib.ptr_array(flow_ups),
+                len(flow_ups), b, h, w, _lib.ptr(ws), ws.numel(), self.precision, _lib.stream()), 'forward_loop')
+
+    def __call__(self, inputs, training, *, last_only=False):
+        """inputs = [image1, image2], each (B, H, W, 3) float in 0..255 on the GPU.
+
+        `training` is required, as in the reference (model.py:68).  `last_only=True` (keyword-only
+        extra) computes just the final prediction -- what predict_step returns (model.py:166)."""
+        image1, image2 = inputs
+        image1, image2 = _lib.f32c(image1), _lib.f32c(image2)
+        bs, H, W, _ = image1.shape
+        if H % 8 or W % 8:
+            raise ValueError(f'image height and width must be multiples of 8 (got {H}x{W}); the reference fails in '
+                             'update.py:146 for other sizes -- crop-or-pad first (datasets/dataset.py:323-334)')
+        h, w = H // 8, W // 8
+        iters = self.iters if training else self.iters_pred                  # model.py:92
+        fmap1, fmap2, net, inp = self._encode(image1, image2, training)
+        corr_block = CorrBlock(fmap1, fmap2, num_levels=self.corr_levels, radius=self.corr_radius,
+                               precision=self.precision)                      # :77-79
+        coords1 = coords_grid(bs, h, w, self.device)                          # :89
+        preds = [torch.empty((bs, H, W, 2), dtype=torch.float32, device=self.device)
+                 if (not last_only or i == iters - 1) else None for i in range(iters)]
+        if iters:
+            self._loop(corr_block, net, inp, coords1, preds, bs, h, w)        # :93-106
+        self._last = dict(net=net, coords1=coords1, corr_block=corr_block)
+        return [p for p in preds if p is not None] if last_only else preds
+
+    call = __call__
+
+    # -- keras-style steps (model.py:111-170) ---------------------------------------------------
+    def compile(self, optimizer=None, clip_norm=None, loss=sequence_loss, epe=end_point_error, **kwargs):
+        self.optimizer = optimizer
+        self.clip_norm = clip_norm
+        self.loss = loss
+        self.epe = epe
+        self.flow_metrics = OrderedDict((k, [0.0, 0]) for k in ('loss', 'epe', 'u1', 'u3', 'u5'))
+
+    def _metric_update(self, key, value):
+        m = self.flow_metrics[key]
+        m[0] += float(value)
+        m[1] += 1
+
+    def _metric_results(self):
+        return {k: (s / n if n else 0.0) for k, (s, n) in self.flow_metrics.items()}
+
+    def train_step(self, data):
+        raise NotImplementedError(
+            'train_step needs the backward pass of the CUDA kernels (SURVEY.md section 8(f) rank 2); this round '
+            'implements the forward/update hot path only')
+
+    def test_step(self, data):
+        """model.py:146-159."""
+        if self.flow_metrics is None:
+            self.compile()
+        image1, image2, flow, valid = data
+        preds = self([image1, image2], training=False, last_only=True)
+        info = self.epe([flow, valid], preds[-1])
+        for k in ('epe', 'u1', 'u3', 'u5'):
+            self._metric_update(k, info[k])
+        return self._metric_results()
+
+    def predict_step(self, data):
+        """model.py:161-166: only the finest prediction."""
+        image1, image2, *_ = data
+        return self([image1, image2], training=False, last_only=True)[-1]
+
+    def reset_metrics(self):
+        if self.flow_metrics is not None:
+            for m in self.flow_metrics.values():
+                m[0], m[1] = 0.0, 0
+
+
+class SmallRAFT(RAFT):
+    _variant = _lib.VARIANT_SMALL
+
+    def _build_layers(self, seed):
+        self.hidden_dim = 96
+        self.context_dim = 64
+        self.corr_levels = 4
+        self.corr_radius = 3
+        s = 0 if seed is None else seed
+        self.fnet = SmallEncoder(output_dim=128, norm_type='instance', drop_rate=self.drop_rate, device=self.device,
+                                 seed=s)
+        self.cnet = SmallEncoder(output_dim=self.hidden_dim + self.context_dim, norm_type=None,
+                                 drop_rate=self.drop_rate, device=self.device, seed=s + 1)
+        self.update_block = SmallUpdateBlock(filters=self.hidden_dim, precision=self.precision, device=self.device,
+                                             seed=s + 2)
+
+    def upsample_flow(self, flow, mask=None):
+        """SmallRAFT upsamples with upflow8 (model.py:223)."""
+        return upflow8(flow)

@@ -1,0 +1,59 @@
+"""Batch-axis data parallelism over the GPUs of one NVSwitch box.
+
+Every sample's correlation volume, lookups and GRU state are independent (corr.py:156-160 is a per-sample
+batched matmul), so inference shards the batch with NO collective on the data path: one process per GPU,
+each runs its contiguous slice.  `torch.distributed` is only used for the optional gather of results and
+for timing barriers.  (The training-step gradient all-reduce belongs to SURVEY.md section 8(f) rank 2.)
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(global_batch, rank, world_size):
+    """Contiguous [lo, hi) slice of the batch owned by `rank`; remainders go to the lowest ranks."""
+    if world_size < 1 or not (0 <= rank < world_size):
+        raise ValueError(f'bad rank/world_size: {rank}/{world_size}')
+    base, rem = divmod(global_batch, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_batch(tensors, rank, world_size):
+    """Slice every (B, ...) tensor of `tensors` to this rank's part of the batch."""
+    lo, hi = shard_bounds(tensors[0].shape[0], rank, world_size)
+    return [t[lo:hi] for t in tensors]
+
+
+def gather_batch(local, global_batch, group=None):
+    """All-gather per-rank (b_r, ...) results back into a (B, ...) tensor in batch order (uneven shards ok)."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    sizes = [shard_bounds(global_batch, r, world) for r in range(world)]
+    max_b = max(hi - lo for lo, hi in sizes)
+    pad = torch.zeros((max_b,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    return torch.cat([p[:hi - lo] for p, (lo, hi) in zip(parts, sizes)], dim=0)
+
+
+def predict_sharded(predict_fn, image1, image2, group=None):
+    """Run `predict_fn(image1_shard, image2_shard) -> (b_r, H, W, 2)` on this rank's shard of a replicated
+    global batch and return the gathered (B, H, W, 2) result on every rank."""
+    if dist.is_available() and dist.is_initialized():
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+    else:
+        rank, world = 0, 1
+    s1, s2 = shard_batch([image1, image2], rank, world)
+    out = predict_fn(s1, s2)
+    return gather_batch(out, image1.shape[0], group)
+
+
+def max_over_ranks(value, device, group=None):
+    """max of a python float over all ranks (timing: a multi-GPU step takes as long as its slowest rank)."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return float(t.item())

@@ -9,6 +9,7 @@ N > 1 is launched by torchrun (one rank per GPU): the batch axis shards with no 
 (weak scaling: 4 pairs per GPU).  Prints ONE JSON line (rank 0).
 """
 import argparse
+import faulthandler
 import json
 import os
 import subprocess
@@ -34,6 +35,18 @@ UPDATE_MAC_PER_PX = 3_118_336                     # BasicUpdateBlock, update.py:
 CORR_FLOP_PER_PAIR = 2 * PX * PX * 256
 CORR_BYTES_PER_PAIR = 4 * sum(PX * ((H // 8) >> l) * ((W // 8) >> l) for l in range(4)) + 8 * PX * 256
 LOOKUP_BYTES_PER_PAIR_ITER = PX * 2904
+
+
+def log(msg):
+    """progress on stderr (stdout carries only the JSON line)"""
+    print(f'[bench {time.strftime("%H:%M:%S")}] {msg}', file=sys.stderr, flush=True)
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
 
 
 def load_peaks():
@@ -88,7 +101,7 @@ def oracle_forward_time(n_pairs, steps, warmup):
     """Time the CPU restatement of the reference forward (oracle/raft_torch.py) on all host cores."""
     import cases
     from oracle import raft_torch as rt, weights
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     torch.set_num_threads(cores)
     p = weights.init_params('raft', 1234)
     im1, im2 = cases.images(n_pairs, H, W)
@@ -175,8 +188,11 @@ def run_ours(args):
         barrier()
         return parallel.max_over_ranks(dev_s, device), parallel.max_over_ranks(wall, device)
 
+    log('model and inputs ready; warm-up')
     for i in range(args.warmup):
         step_resident(i)
+    torch.cuda.synchronize()
+    log('warm-up done; timing device-resident steps')
     _lib.launch_count_reset()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -186,6 +202,7 @@ def run_ours(args):
     launches = _lib.launch_count()
     value = world * B_PER_GPU * args.steps / dev_s
 
+    log(f'resident: {value:.1f} pairs/s; timing end-to-end steps')
     for i in range(min(args.warmup, 2)):
         step_e2e(i)
     _, e2e_wall = timed(step_e2e, args.steps)
@@ -196,6 +213,7 @@ def run_ours(args):
     line = None
     if rank == 0:
         peaks = load_peaks()
+        log(f'e2e: {e2e_value:.1f} pairs/s; kernel-level timings')
         # --- kernel-level timing for the roofline objects (rank 0, CUDA events on the launching stream) ---
         a, b = dev_in[0]
         fmap1, fmap2, net, inp = model._encode(a, b, False)
@@ -231,6 +249,7 @@ def run_ours(args):
         corr_bytes = B_PER_GPU * (CORR_BYTES_PER_PAIR + ITERS * LOOKUP_BYTES_PER_PAIR_ITER)
         ach_gbs = corr_bytes / (t_corr + ITERS * t_lookup) / 1e9
 
+        log('parity check of the timed configuration against the oracle')
         # --- parity of the timed configuration against the oracle (one pair of batch 0) ---
         from oracle import raft_torch as rt
         im1, im2 = cases.images(B_PER_GPU, H, W, 0, 1)
@@ -238,6 +257,7 @@ def run_ours(args):
         got = model([dev_in[0][0][:1], dev_in[0][1][:1]], training=False, last_only=True)[-1].cpu()
         max_abs = float((got - want).abs().max())
 
+        log(f'max-abs {max_abs:.2e}; CPU baseline')
         # --- CPU baseline: the restated reference on the host cores, bounded sample ---
         cpu_pps, cpu_sec, cores, _ = oracle_forward_time(1, 3, 1)
 
@@ -287,6 +307,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--precision', default=os.environ.get('RAFT_B200_PRECISION', 'f16x2'), choices=['f16x2', 'fp32'])
     args = ap.parse_args()
+    faulthandler.enable()
+    faulthandler.dump_traceback_later(420, exit=False)     # a hang leaves stack traces on stderr
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else max(args.warmup, 1)
     if args.impl == 'reference':
         run_reference(args)

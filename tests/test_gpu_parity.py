@@ -112,9 +112,9 @@ def test_update_block_ragged_grid(T, precision):
     ops = rt.Ops(p)
     t = [torch.from_numpy(a).permute(0, 3, 1, 2) for a in (net, inp, corr, flow)]
     on, om, od = rt.basic_update_block(ops, *t)
-    np.testing.assert_allclose(n2.cpu().numpy(), on.permute(0, 2, 3, 1).numpy(), atol=2e-5, rtol=1e-4)
-    np.testing.assert_allclose(delta.cpu().numpy(), od.permute(0, 2, 3, 1).numpy(), atol=5e-5, rtol=1e-4)
-    np.testing.assert_allclose(mask.cpu().numpy(), om.permute(0, 2, 3, 1).numpy(), atol=5e-5, rtol=1e-4)
+    np.testing.assert_allclose(n2.cpu().numpy(), on.permute(0, 2, 3, 1).numpy(), atol=1e-4, rtol=1e-4)
+    np.testing.assert_allclose(delta.cpu().numpy(), od.permute(0, 2, 3, 1).numpy(), atol=2e-4, rtol=1e-4)
+    np.testing.assert_allclose(mask.cpu().numpy(), om.permute(0, 2, 3, 1).numpy(), atol=2e-4, rtol=1e-4)
 
 
 def test_upsample_convex_vs_oracle(T):

@@ -12,6 +12,20 @@ import torch
 import torch.nn.functional as F
 
 
+def force_ieee_fp32():
+    """fp32 convolutions must really be fp32: PyTorch's cuDNN default is TF32 (10-bit mantissa), which alone
+    moves the final flow by ~1 px (DESIGN.md "Precision").  Process-wide torch setting."""
+    try:
+        torch.backends.cudnn.conv.fp32_precision = 'ieee'
+        torch.backends.cuda.matmul.fp32_precision = 'ieee'
+    except Exception:                      # older PyTorch: legacy switches
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+
+
+force_ieee_fp32()
+
+
 def _same_pads(n_in, k, s):
     n_out = -(-n_in // s)
     total = max((n_out - 1) * s + k - n_in, 0)
@@ -64,8 +78,7 @@ class _Params:
             pl, pr = _same_pads(x.shape[3], w.shape[3], stride)
             if pt or pb or pl or pr:
                 x = F.pad(x, (pl, pr, pt, pb))
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-            return F.conv2d(x, w, self.params[name + '.bias'], stride=stride)
+        return F.conv2d(x, w, self.params[name + '.bias'], stride=stride)
 
     def norm(self, x, name, norm_type, training):
         eps = 1e-3        # tfa InstanceNormalization and keras BatchNormalization both default to 1e-3

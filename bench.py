@@ -101,8 +101,7 @@ def oracle_forward_time(n_pairs, steps, warmup):
     """Time the CPU restatement of the reference forward (oracle/raft_torch.py) on all host cores."""
     import cases
     from oracle import raft_torch as rt, weights
-    cores = host_cores()
-    torch.set_num_threads(cores)
+    cores = torch.get_num_threads()      # PyTorch's own intra-op pool size; resizing it after use can stall oneDNN
     p = weights.init_params('raft', 1234)
     im1, im2 = cases.images(n_pairs, H, W)
     for _ in range(warmup):

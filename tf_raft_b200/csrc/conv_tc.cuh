@@ -11,10 +11,15 @@
 //   by tcgen05.mma (kind::f16, M=128, N=bn, K=16); the fp32 accumulator lives in TMEM.
 // * fp32-grade arithmetic from fp16 tensor cores: each operand is a (hi, lo) fp16 pair and every
 //   K step issues hi*hi, lo*hi, hi*lo into the same accumulator (DESIGN.md "Precision").
+// * Tensor-core fp32 accumulation truncates (measured: ~0.6 ulp of bias per K=16 step, all towards
+//   zero), so a 1920-deep GRU contraction issued as one 360-step chain is ~60x less accurate than an
+//   FFMA chain.  The K loop is therefore cut into groups of `group_chunks` 64-channel chunks; each
+//   group accumulates into one of two TMEM buffers (ping-pong) and is then promoted -- added in IEEE
+//   fp32 -- into per-thread register accumulators while the next group runs on the tensor core.
 // * Warp roles: warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA issuer (one
-//   elected lane), warps 2..5 = epilogue (TMEM -> registers -> fused bias / activation / GRU gating /
-//   hi-lo re-split -> global).  smem full/empty mbarrier ring between producer and issuer,
-//   tcgen05.commit -> mbarrier between issuer and epilogue.
+//   elected lane), warps 2..9 = promotion + epilogue (TMEM -> registers, then fused bias / activation /
+//   GRU gating / hi-lo re-split -> global).  mbarrier rings: smem full/empty (producer <-> issuer),
+//   TMEM full/empty (issuer <-> promotion warps).
 #pragma once
 #include "common.cuh"
 #include "tmap.cuh"
@@ -29,7 +34,7 @@ enum TcEpilogue : int {
 };
 enum TcAct : int { ACT_NONE = 0, ACT_RELU = 1 };
 
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 320;           // 1 producer + 1 issuer + 8 promotion/epilogue warps
 constexpr int kTileM = 128;
 constexpr int kChunkK = 64;                       // fp16 elements per 128-byte swizzled row
 constexpr int kABytes = kTileM * kChunkK * 2;     // 16 KiB per A plane per stage
@@ -43,6 +48,7 @@ struct alignas(64) TcConvParams {
   int B, H, W, TH, TW, tiles_x, tiles_y;
   int bn, n_total;                // N per CTA (multiple of 16, <= 256); total valid output columns
   int nstages, stage_bytes, tmem_cols;
+  int group_chunks;               // K chunks per promotion group (accumulation chain = 12 * group_chunks MMAs)
   int b_batch_stride;             // B-map coordinate 2 = tap + b * b_batch_stride (correlation: 1, taps = 1)
   int mode, act;
   const float* bias;              // [n_total padded to bn multiple]; may be null
@@ -94,8 +100,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
   const int b_bytes = p.bn * kChunkK * 2;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)nst * p.stage_bytes);
   uint64_t* empty_bar = full_bar + nst;
-  uint64_t* accum_bar = empty_bar + nst;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint64_t* acc_full = empty_bar + nst;      // [2] issuer -> promotion warps
+  uint64_t* acc_empty = acc_full + 2;        // [2] promotion warps -> issuer
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -111,13 +118,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
   const int ntaps = p.kh * p.kw;
   const int chunks_per_tap = p.seg_chunks[0] + (p.nseg > 1 ? p.seg_chunks[1] : 0);
   const int total = ntaps * chunks_per_tap;
+  const int gsz = p.group_chunks;
+  const int ngroups = (total + gsz - 1) / gsz;
+  const int nchunks32 = (p.bn + 31) >> 5;                 // 32-column accumulator chunks
+  const int chunks_a = (nchunks32 + 1) >> 1;              // handled by warps 2..5; the rest by warps 6..9
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < nst; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(accum_bar, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], nchunks32 > 1 ? 8 : 4);    // one arrival per participating warp
+    }
     fence_mbar_init();
     prefetch_tmap(&p.a_hi[0]);
     prefetch_tmap(&p.a_lo[0]);
@@ -164,64 +178,100 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     const uint32_t idesc = make_idesc_f16(kTileM, p.bn);
-    for (int it = 0; it < total; ++it) {
-      const int s = it % nst;
-      const uint32_t phase = (uint32_t)(it / nst) & 1u;
-      mbar_wait(&full_bar[s], phase);
+    int it = 0;
+    for (int g = 0; g < ngroups; ++g) {
+      const int buf = g & 1;
+      mbar_wait(&acc_empty[buf], ((uint32_t)(g >> 1) & 1u) ^ 1u);   // promotion warps drained this buffer
       tc_fence_after();
-      if (elect_one()) {
-        const uint32_t sa = smem_u32(smem + (size_t)s * p.stage_bytes);
-        const uint64_t a_hi = make_desc_sw128(sa);
-        const uint64_t a_lo = make_desc_sw128(sa + kABytes);
-        const uint64_t b_hi = make_desc_sw128(sa + 2 * kABytes);
-        const uint64_t b_lo = make_desc_sw128(sa + 2 * kABytes + b_bytes);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.bn);
+      const int gend = min(total, (g + 1) * gsz);
+      for (int first = 1; it < gend; ++it, first = 0) {
+        const int s = it % nst;
+        const uint32_t phase = (uint32_t)(it / nst) & 1u;
+        mbar_wait(&full_bar[s], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + (size_t)s * p.stage_bytes);
+          const uint64_t a_hi = make_desc_sw128(sa);
+          const uint64_t a_lo = make_desc_sw128(sa + kABytes);
+          const uint64_t b_hi = make_desc_sw128(sa + 2 * kABytes);
+          const uint64_t b_lo = make_desc_sw128(sa + 2 * kABytes + b_bytes);
 #pragma unroll
-        for (int k = 0; k < kChunkK / 16; ++k)   // +32 bytes per K=16 step == +2 in 16-byte units
-          umma_f16(tmem_base, a_hi + 2 * k, b_hi + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < kChunkK / 16; ++k)   // +32 bytes per K=16 step == +2 in 16-byte units
+            umma_f16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (!first || k > 0) ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < kChunkK / 16; ++k) umma_f16(tmem_base, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+          for (int k = 0; k < kChunkK / 16; ++k) umma_f16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
 #pragma unroll
-        for (int k = 0; k < kChunkK / 16; ++k) umma_f16(tmem_base, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
-        umma_commit(&empty_bar[s]);                 // frees the smem slot once these MMAs retire
-        if (it == total - 1) umma_commit(accum_bar);  // accumulator complete -> epilogue
+          for (int k = 0; k < kChunkK / 16; ++k) umma_f16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+          umma_commit(&empty_bar[s]);                    // frees the smem slot once these MMAs retire
+          if (it == gend - 1) umma_commit(&acc_full[buf]);   // group complete -> promotion warps
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== promotion + epilogue (warps 2..9) =====================
     const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;                // 0: chunks [0, chunks_a), 1: chunks [chunks_a, nchunks32)
+    const int chunk0 = half ? chunks_a : 0;
+    const int my_chunks = half ? (nchunks32 - chunks_a) : chunks_a;
     const int m = quarter * 32 + lane;               // tile row == TMEM lane
     const int xl = m % p.TW, yl = m / p.TW;
     const int x = x0 + xl, y = y0 + yl;
     const bool valid = (x < p.W) && (y < p.H);
     const size_t pix = ((size_t)b * p.H + (valid ? y : 0)) * p.W + (valid ? x : 0);
     const float inv_scale = p.inv_scale ? __ldg(p.inv_scale) : 1.0f;
-
-    mbar_wait(accum_bar, 0);
-    tc_fence_after();
     const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
 
-    for (int c0 = 0; c0 < p.bn; c0 += 32) {
-      const int ncol = min(32, p.bn - c0);           // bn is a multiple of 16: 32 or 16
-      uint32_t r[32];
-      if (ncol == 32) {
-        tmem_ld_32x32(trow + (uint32_t)c0, r);
-      } else {
-        uint32_t r16[16];
-        tmem_ld_32x16(trow + (uint32_t)c0, r16);
+    float racc[4][32];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) r[j] = r16[j];
+    for (int ci = 0; ci < 4; ++ci)
 #pragma unroll
-        for (int j = 16; j < 32; ++j) r[j] = 0u;
+      for (int j = 0; j < 32; ++j) racc[ci][j] = 0.0f;
+
+    if (my_chunks > 0) {
+      for (int g = 0; g < ngroups; ++g) {
+        const int buf = g & 1;
+        mbar_wait(&acc_full[buf], (uint32_t)(g >> 1) & 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+          if (ci < my_chunks) {
+            const int c0 = (chunk0 + ci) * 32;
+            uint32_t r[32];
+            if (p.bn - c0 >= 32) {
+              tmem_ld_32x32(trow + (uint32_t)(buf * p.bn + c0), r);
+            } else {
+              uint32_t r16[16];
+              tmem_ld_32x16(trow + (uint32_t)(buf * p.bn + c0), r16);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) r[j] = r16[j];
+#pragma unroll
+              for (int j = 16; j < 32; ++j) r[j] = 0u;
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) racc[ci][j] += __uint_as_float(r[j]);   // IEEE fp32 promotion
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
       }
-      tmem_ld_wait();
+    }
+
+#pragma unroll
+    for (int ci = 0; ci < 4; ++ci) {
+      if (ci >= my_chunks) continue;
+      const int c0 = (chunk0 + ci) * 32;
+      const int ncol = min(32, p.bn - c0);           // bn is a multiple of 16: 32 or 16
       if (!valid) continue;
       const int col = n0 + c0;                       // first global output column of this chunk
       float v[32];
 
       if (p.mode == EPI_CORR) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __fdiv_rn(__uint_as_float(r[j]), p.corr_div);
+        for (int j = 0; j < 32; ++j) v[j] = __fdiv_rn(racc[ci][j], p.corr_div);
         const int nvalid = min(ncol, p.n_total - col);
         if (nvalid > 0) {
           float* dst = p.out_f32 + pix * (size_t)p.f32_stride + col;
@@ -232,7 +282,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
 
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        float t = __uint_as_float(r[j]) * inv_scale;
+        float t = racc[ci][j] * inv_scale;
         if (p.bias) t += __ldg(p.bias + col + j);
         v[j] = t;
       }
@@ -331,9 +381,10 @@ inline int tc_finalize(TcConvParams& p) {
   if (nst > 8) nst = 8;
   p.nstages = nst;
   int cols = 32;
-  while (cols < p.bn) cols <<= 1;
+  while (cols < 2 * p.bn) cols <<= 1;           // two accumulator buffers (ping-pong promotion)
   p.tmem_cols = cols;
-  return nst * p.stage_bytes + 1024 /*align slack*/ + (2 * nst + 1) * 8 + 16;
+  if (p.group_chunks <= 0) p.group_chunks = 2;
+  return nst * p.stage_bytes + 1024 /*align slack*/ + (2 * nst + 4) * 8 + 16;
 }
 
 inline int tc_launch(TcConvParams& p, int n_tiles_n, cudaStream_t stream) {

@@ -145,6 +145,56 @@ int raft_b200_update_small(const void* prepared, const float* net, const float* 
                            void* workspace, size_t workspace_bytes, int precision, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Encoders  (tf_raft/layers/extractor.py) -- SURVEY.md section 8(f) rank 1
+ * ------------------------------------------------------------------------------------------- */
+
+/* One normalisation layer: tfa InstanceNormalization (gamma, beta) or keras BatchNormalization (+ moving
+ * statistics); all (C,) device pointers; NULL members for norm_type NONE.  eps = 1e-3 (extractor.py:6-16).   */
+typedef struct raft_norm {
+  const float* gamma;
+  const float* beta;
+  const float* moving_mean;
+  const float* moving_variance;
+} raft_norm;
+
+/* ResBlock (extractor.py:19-49); downsample.kernel == NULL when strides == 1.                              */
+typedef struct raft_resblock {
+  raft_conv conv1, conv2;
+  raft_norm norm1, norm2;
+  raft_conv downsample;
+  raft_norm downsample_norm;
+} raft_resblock;
+
+/* BasicEncoder / SmallEncoder (extractor.py:88-175): conv1 7x7 s2, norm1, layer1..3 (2 ResBlocks each,
+ * in order layer1.0, layer1.1, layer2.0, ...), conv2 1x1.                                                   */
+typedef struct raft_encoder_weights {
+  raft_conv conv1;
+  raft_norm norm1;
+  raft_resblock block[6];
+  raft_conv conv2;
+} raft_encoder_weights;
+
+typedef enum raft_norm_type { RAFT_NORM_NONE = 0, RAFT_NORM_INSTANCE = 1, RAFT_NORM_BATCH = 2 } raft_norm_type;
+
+int raft_b200_encoder_prepared_bytes(int variant, int out_dim, size_t* bytes);
+int raft_b200_encoder_prepare(int variant, int norm_type, int out_dim, const raft_encoder_weights* weights,
+                              void* prepared, size_t prepared_bytes, void* stream);
+int raft_b200_encoder_workspace_bytes(int variant, int N, int H, int W, size_t* bytes);
+
+/* BasicEncoder.call / SmallEncoder.call (extractor.py:113-130 / 158-175) on N images.
+ *   images : (N, H, W, 3); image_norm != 0: values are 0..255 and the 2*(x/255)-1 of model.py:70-71 is
+ *            fused into the first load; image_norm == 0: already normalised (the encoder layer on its own)
+ *   out    : (N, ceil(H/8), ceil(W/8), out_dim)
+ *   training != 0 selects batch statistics for RAFT_NORM_BATCH (moving statistics are not updated here).   */
+int raft_b200_encoder_forward(int variant, int norm_type, int out_dim, const void* prepared, const float* images,
+                              int N, int H, int W, int training, int image_norm, float* out, void* workspace,
+                              size_t workspace_bytes, void* stream);
+
+/* model.py:84-86: net = tanh(cnet[..., :hidden]), inp = relu(cnet[..., hidden:]).                          */
+int raft_b200_context_split(const float* cnet, int npix, int hidden, int context, float* net, float* inp,
+                            void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Model loop  (tf_raft/model.py)
  * ------------------------------------------------------------------------------------------- */
 

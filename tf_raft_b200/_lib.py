@@ -37,6 +37,25 @@ class RaftConv(ctypes.Structure):
                 ('kh', ctypes.c_int), ('kw', ctypes.c_int), ('cin', ctypes.c_int), ('cout', ctypes.c_int)]
 
 
+class RaftNorm(ctypes.Structure):
+    """struct raft_norm"""
+    _fields_ = [('gamma', ctypes.c_void_p), ('beta', ctypes.c_void_p), ('moving_mean', ctypes.c_void_p),
+                ('moving_variance', ctypes.c_void_p)]
+
+
+class RaftResBlock(ctypes.Structure):
+    """struct raft_resblock"""
+    _fields_ = [('conv1', RaftConv), ('conv2', RaftConv), ('norm1', RaftNorm), ('norm2', RaftNorm),
+                ('downsample', RaftConv), ('downsample_norm', RaftNorm)]
+
+
+class RaftEncoderWeights(ctypes.Structure):
+    """struct raft_encoder_weights"""
+    _fields_ = [('conv1', RaftConv), ('norm1', RaftNorm), ('block', RaftResBlock * 6), ('conv2', RaftConv)]
+
+
+NORM_TYPES = {None: 0, 'instance': 1, 'batch': 2}
+
 _vp, _i, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
 _SIGNATURES = {
     'raft_b200_strerror': (ctypes.c_char_p, [_i]),
@@ -57,6 +76,11 @@ _SIGNATURES = {
     'raft_b200_update_small': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _i, _vp]),
     'raft_b200_upsample_convex': (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     'raft_b200_upflow8': (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    'raft_b200_encoder_prepared_bytes': (_i, [_i, _i, ctypes.POINTER(_sz)]),
+    'raft_b200_encoder_prepare': (_i, [_i, _i, _i, _vp, _vp, _sz, _vp]),
+    'raft_b200_encoder_workspace_bytes': (_i, [_i, _i, _i, _i, ctypes.POINTER(_sz)]),
+    'raft_b200_encoder_forward': (_i, [_i, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    'raft_b200_context_split': (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     'raft_b200_forward_loop': (_i, [_i, _vp, ctypes.POINTER(_vp), _i, _i, _vp, _vp, _vp, ctypes.POINTER(_vp), _i,
                                     _i, _i, _i, _vp, _sz, _i, _vp]),
 }

@@ -1,7 +1,7 @@
 // extern "C" entry points of libraft_b200.so (see include/raft_b200.h for the contract and the
 // reference file:line each one replaces).  Host code only decides shapes and launches kernels;
 // there is no CPU compute path.
-#include "update.cuh"
+#include "encoder.cuh"
 
 namespace raft {
 thread_local long long g_launches = 0;
@@ -591,6 +591,50 @@ int raft_b200_upflow8(const float* flow, int B, int h, int w, float* out, void* 
   if (!flow || !out) return RAFT_ERR_BAD_ARG;
   RAFT_TRY(check_dims(B, h, w));
   upflow8_kernel<<<grid_for((size_t)B * h * w * 64), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(flow, B, h, w, out);
+  RAFT_COUNT_LAUNCH();
+  return raft_launch_status();
+}
+
+int raft_b200_encoder_prepared_bytes(int variant, int out_dim, size_t* bytes) {
+  if (!bytes || (variant != RAFT_VARIANT_BASIC && variant != RAFT_VARIANT_SMALL)) return RAFT_ERR_BAD_ARG;
+  if (out_dim < 32 || out_dim > 256 || out_dim % 32) return RAFT_ERR_BAD_SHAPE;
+  *bytes = enc_layout(variant, out_dim).total;
+  return RAFT_OK;
+}
+
+int raft_b200_encoder_prepare(int variant, int norm_type, int out_dim, const raft_encoder_weights* weights,
+                              void* prepared, size_t prepared_bytes, void* stream) {
+  if (!weights || !prepared || (variant != RAFT_VARIANT_BASIC && variant != RAFT_VARIANT_SMALL)) return RAFT_ERR_BAD_ARG;
+  if (norm_type < 0 || norm_type > 2) return RAFT_ERR_BAD_ARG;
+  if (out_dim < 32 || out_dim > 256 || out_dim % 32) return RAFT_ERR_BAD_SHAPE;
+  return encoder_prepare(variant, norm_type, out_dim, weights, prepared, prepared_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int raft_b200_encoder_workspace_bytes(int variant, int N, int H, int W, size_t* bytes) {
+  if (!bytes || (variant != RAFT_VARIANT_BASIC && variant != RAFT_VARIANT_SMALL)) return RAFT_ERR_BAD_ARG;
+  RAFT_TRY(check_dims(N, H, W));
+  *bytes = enc_ws_layout(nullptr, variant, N, H, W).total;
+  return RAFT_OK;
+}
+
+int raft_b200_encoder_forward(int variant, int norm_type, int out_dim, const void* prepared, const float* images,
+                              int N, int H, int W, int training, int image_norm, float* out, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  if (!prepared || !images || !out || !workspace) return RAFT_ERR_BAD_ARG;
+  if (variant != RAFT_VARIANT_BASIC && variant != RAFT_VARIANT_SMALL) return RAFT_ERR_BAD_ARG;
+  if (norm_type < 0 || norm_type > 2) return RAFT_ERR_BAD_ARG;
+  RAFT_TRY(check_dims(N, H, W));
+  if (out_dim < 32 || out_dim > 256 || out_dim % 32 || H < 8 || W < 8) return RAFT_ERR_BAD_SHAPE;
+  return encoder_forward(variant, norm_type, out_dim, prepared, images, N, H, W, training, image_norm, out, workspace, workspace_bytes,
+                         reinterpret_cast<cudaStream_t>(stream));
+}
+
+int raft_b200_context_split(const float* cnet, int npix, int hidden, int context, float* net, float* inp,
+                            void* stream) {
+  if (!cnet || !net || !inp) return RAFT_ERR_BAD_ARG;
+  if (npix < 1 || hidden < 1 || context < 1) return RAFT_ERR_BAD_SHAPE;
+  context_split_kernel<<<grid_for((size_t)npix * (hidden + context)), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      cnet, (size_t)npix, hidden, context, net, inp);
   RAFT_COUNT_LAUNCH();
   return raft_launch_status();
 }

@@ -45,6 +45,7 @@ struct alignas(64) TcConvParams {
   CUtensorMap b_hi, b_lo;
   int nseg, seg_chunks[2], seg_c0[2];
   int kh, kw, ph, pw;             // taps and 'same' padding (pad before)
+  int stride;                     // 1 or 2: input pixel = output pixel * stride + tap - pad (TMA elementStrides)
   int B, H, W, TH, TW, tiles_x, tiles_y;
   int bn, n_total;                // N per CTA (multiple of 16, <= 256); total valid output columns
   int nstages, stage_bytes, tmem_cols;
@@ -57,6 +58,9 @@ struct alignas(64) TcConvParams {
   float corr_div;                 // EPI_CORR: sqrt(C)
   float* out_f32; int f32_stride, f32_c0;
   __half* out_hi; __half* out_lo; int h_stride, h_c0;
+  const float* post_scale;        // EPI_LINEAR: optional per-column affine after the bias (folded BatchNorm):
+  const float* post_shift;        //   v = v * post_scale[col] + post_shift[col]
+  const float* residual; int res_stride, res_c0;   // EPI_LINEAR: optional skip input: v = relu(act(v) + residual)
   const float* concat_src; int concat_n;   // EPI_LINEAR: fp32 (px, concat_n) appended at columns [n_total, n_total+concat_n)
   float* z; int hid;                       // GRU: z plane (px, hid) fp32
   float* h;                                // GRU: hidden state (px, hid) fp32, updated in place by EPI_GRU_Q
@@ -166,8 +170,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
             uint8_t* st = smem + (size_t)s * p.stage_bytes;
             mbar_arrive_expect_tx(&full_bar[s], (uint32_t)p.stage_bytes);
             const int c = p.seg_c0[seg] + ch * kChunkK;
-            tma_load_4d(st, &p.a_hi[seg], &full_bar[s], c, x0 + dx, y0 + dy, b);
-            tma_load_4d(st + kABytes, &p.a_lo[seg], &full_bar[s], c, x0 + dx, y0 + dy, b);
+            tma_load_4d(st, &p.a_hi[seg], &full_bar[s], c, x0 * p.stride + dx, y0 * p.stride + dy, b);
+            tma_load_4d(st + kABytes, &p.a_lo[seg], &full_bar[s], c, x0 * p.stride + dx, y0 * p.stride + dy, b);
             const int tcoord = tap + b * p.b_batch_stride;
             tma_load_3d(st + 2 * kABytes, &p.b_hi, &full_bar[s], kc * kChunkK, n0, tcoord);
             tma_load_3d(st + 2 * kABytes + b_bytes, &p.b_lo, &full_bar[s], kc * kChunkK, n0, tcoord);
@@ -284,6 +288,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       for (int j = 0; j < 32; ++j) {
         float t = racc[ci][j] * inv_scale;
         if (p.bias) t += __ldg(p.bias + col + j);
+        if (p.post_scale) t = t * __ldg(p.post_scale + col + j) + __ldg(p.post_shift + col + j);
         v[j] = t;
       }
 
@@ -293,6 +298,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
           float t = v[j];
           if (p.act == ACT_RELU) t = fmaxf(t, 0.0f);
           t *= p.out_scale;
+          if (p.residual && col + j < p.n_total)
+            t = fmaxf(t + __ldg(p.residual + pix * (size_t)p.res_stride + p.res_c0 + col + j), 0.0f);
           if (col + j >= p.n_total) {                // padded columns: concat tail, else exact zeros
             const int cj = col + j - p.n_total;
             t = (p.concat_src && cj < p.concat_n) ? __ldg(p.concat_src + pix * p.concat_n + cj) : 0.0f;
@@ -389,6 +396,7 @@ inline int tc_finalize(TcConvParams& p) {
 
 inline int tc_launch(TcConvParams& p, int n_tiles_n, cudaStream_t stream) {
   if (p.bn % 16 != 0 || p.bn < 16 || p.bn > 256 || p.TW * p.TH != kTileM) return RAFT_ERR_BAD_SHAPE;
+  if (p.stride < 1) p.stride = 1;
   const int smem = tc_finalize(p);
   if (p.nstages < 2) return RAFT_ERR_UNSUPPORTED;
   static bool attr_set = false;   // benign race: idempotent

@@ -200,7 +200,10 @@ struct SimtConvParams {
   const float* src[3]; int src_stride[3], src_c0[3], src_n[3]; int nsrc;
   const float* w; const float* bias;         // HWIO (kh, kw, cin, cout)
   int kh, kw, cin, cout;
-  int B, H, W;
+  int B, H, W;                               // OUTPUT grid
+  int stride, Hin, Win, pad_t, pad_l;        // stride 0/1 => stride 1, input grid = output grid, symmetric 'same' pads
+  int in_image_norm;                         // 1: input is a 0..255 image, normalised on load as 2*(x/255)-1 (model.py:70-71)
+  const float* post_scale; const float* post_shift;   // optional per-cout affine after the bias (folded BatchNorm)
   float* out; int out_stride, out_c0;
   __half* out_hi; __half* out_lo; int h_stride, h_c0;   // optional fp16 hi/lo copy of the output
   int act; float out_scale;
@@ -214,7 +217,9 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const SimtConvParams p) 
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int lr = threadIdx.x >> 2, lc = (threadIdx.x & 3) * 4;   // A loader: pixel row, 4 channels
   const int wr = threadIdx.x >> 4, wc = (threadIdx.x & 15) * 4;  // W loader: k row, 4 couts
-  const int ph = (p.kh - 1) / 2, pw = (p.kw - 1) / 2;
+  const int st = p.stride > 1 ? p.stride : 1;
+  const int Hin = p.stride > 0 ? p.Hin : p.H, Win = p.stride > 0 ? p.Win : p.W;
+  const int ph = p.stride > 0 ? p.pad_t : (p.kh - 1) / 2, pw = p.stride > 0 ? p.pad_l : (p.kw - 1) / 2;
   // this thread's loader pixel
   const int lp = m0 + lr;
   int lb = 0, ly = 0, lx = 0;
@@ -226,9 +231,9 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const SimtConvParams p) 
   float acc[4][4] = {};
   for (int tap = 0; tap < p.kh * p.kw; ++tap) {
     const int dy = tap / p.kw - ph, dx = tap % p.kw - pw;
-    const int sy = ly + dy, sx = lx + dx;
-    const bool inb = lp < npix && sy >= 0 && sy < p.H && sx >= 0 && sx < p.W;
-    const size_t spix = ((size_t)lb * p.H + (inb ? sy : 0)) * p.W + (inb ? sx : 0);
+    const int sy = ly * st + dy, sx = lx * st + dx;
+    const bool inb = lp < npix && sy >= 0 && sy < Hin && sx >= 0 && sx < Win;
+    const size_t spix = ((size_t)lb * Hin + (inb ? sy : 0)) * Win + (inb ? sx : 0);
     for (int k0 = 0; k0 < p.cin; k0 += 16) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -238,6 +243,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const SimtConvParams p) 
           int cc = c, s = 0;
           while (s < p.nsrc - 1 && cc >= p.src_n[s]) cc -= p.src_n[s++];
           v = __ldg(p.src[s] + spix * p.src_stride[s] + p.src_c0[s] + cc);
+          if (p.in_image_norm) v = __fsub_rn(__fmul_rn(2.0f, __fdiv_rn(v, 255.0f)), 1.0f);
         }
         As[lc + j][lr] = v;
       }
@@ -275,6 +281,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const SimtConvParams p) 
       const int n = n0 + tx * 4 + j;
       if (n >= p.cout) continue;
       float v = acc[i][j] + (p.bias ? __ldg(p.bias + n) : 0.f);
+      if (p.post_scale) v = v * __ldg(p.post_scale + n) + __ldg(p.post_shift + n);
       if (p.act == SACT_RELU) v = fmaxf(v, 0.f);
       else if (p.act == SACT_SIGMOID) v = sigmoidf_acc(v);
       else if (p.act == SACT_TANH) v = tanhf(v);
@@ -450,6 +457,126 @@ __global__ void pack_weights_kernel(const PackParams p) {
     const size_t o = ((size_t)tap * p.cout_pad + p.cout_off + n) * p.cin_pad + cd;
     p.hi[o] = hh;
     p.lo[o] = ll;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Normalisation layers of the encoders (extractor.py:6-16): tfa InstanceNormalization (statistics per
+// image) / Keras BatchNormalization in training mode (statistics over the batch), eps = 1e-3.
+// y is the raw convolution output (G groups x P pixels x C channels, fp32).  Two deterministic
+// passes: mean, then sum of squared deviations (no E[x^2]-E[x]^2 cancellation).
+//   pass = 0: part[g][split][c] = sum_p y            pass = 1: part[...] = sum_p (y - mean[g][c])^2
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) norm_partial_kernel(const float* __restrict__ y, int P, int C, int nsplit,
+                                                           const float* __restrict__ mean, int pass,
+                                                           float* __restrict__ part) {
+  __shared__ float red[256];
+  const int g = blockIdx.x, sp = blockIdx.y;
+  const int lanes = 256 / C > 0 ? 256 / C : 1;          // pixel lanes per block (C <= 256)
+  const int c = threadIdx.x % C, pl = threadIdx.x / C;
+  const int per = (P + nsplit - 1) / nsplit;
+  const int p0 = sp * per, p1 = min(P, p0 + per);
+  float acc = 0.f;
+  if (pl < lanes) {
+    const float mu = pass ? mean[(size_t)g * C + c] : 0.f;
+    const float* base = y + ((size_t)g * P) * C + c;
+    for (int px = p0 + pl; px < p1; px += lanes) {
+      const float v = base[(size_t)px * C] - mu;
+      acc += pass ? v * v : v;
+    }
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  if (pl == 0) {
+    float tot = 0.f;
+    for (int l = 0; l < lanes; ++l) tot += red[l * C + c];      // fixed order: deterministic
+    part[((size_t)g * nsplit + sp) * C + c] = tot;
+  }
+}
+// pass 0: mean = sum/P.   pass 1: a = rsqrt(sum/P + eps) * gamma   (the multiplier applied to (y - mean)).
+__global__ void norm_final_kernel(const float* __restrict__ part, int G, int C, int nsplit, int P, int pass,
+                                  const float* __restrict__ gamma, float eps, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= G * C) return;
+  const int g = i / C, c = i % C;
+  float tot = 0.f;
+  for (int s = 0; s < nsplit; ++s) tot += part[((size_t)g * nsplit + s) * C + c];
+  out[i] = pass ? rsqrtf(tot / (float)P + eps) * gamma[c] : tot / (float)P;
+}
+// out = [relu]((y - mean) * a + beta);  optional skip: out = relu(skip + out)  (ResBlock, extractor.py:41-49)
+// Writes fp32 (optional) and the fp16 hi/lo operand planes (optional; channels [C, c_pad) zeroed).
+__global__ void norm_apply_kernel(const float* __restrict__ y, size_t npix, int P, int C, int per_image,
+                                  const float* __restrict__ mean, const float* __restrict__ a,
+                                  const float* __restrict__ beta, int relu, const float* __restrict__ skip,
+                                  float* __restrict__ out32, __half* __restrict__ hi, __half* __restrict__ lo,
+                                  int c_pad) {
+  const size_t total = npix * (size_t)c_pad;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t px = i / c_pad;
+    const int c = (int)(i - px * c_pad);
+    float v = 0.f;
+    if (c < C) {
+      const size_t g = per_image ? px / P : 0;
+      v = (y[px * C + c] - mean[g * C + c]) * a[g * C + c] + beta[c];
+      if (relu) v = fmaxf(v, 0.f);
+      if (skip) v = fmaxf(skip[px * C + c] + v, 0.f);
+      if (out32) out32[px * C + c] = v;
+    }
+    if (hi) {
+      __half hh, ll;
+      split_f16(v, hh, ll);
+      hi[i] = hh;
+      lo[i] = ll;
+    }
+  }
+}
+// Stem im2col (extractor.py:95, model.py:70-71): for every output pixel of the 7x7 stride-2 'same' convolution,
+// the 147 input values (tap-major, then rgb) of its window, normalised 2*(x/255)-1, zero outside the image
+// (padding applies to the normalised image), as fp16 hi/lo planes with 192 channels (147..191 = 0).
+__global__ void stem_im2col_kernel(const float* __restrict__ img, int N, int H, int W, int h, int w, int pad_t,
+                                   int pad_l, int image_norm, __half* __restrict__ hi, __half* __restrict__ lo) {
+  const size_t total = (size_t)N * h * w * 192;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int kk = (int)(i % 192);
+    size_t px = i / 192;
+    const int x = (int)(px % w), y = (int)((px / w) % h), n = (int)(px / ((size_t)w * h));
+    float v = 0.f;
+    if (kk < 147) {
+      const int tap = kk / 3, c = kk - tap * 3;
+      const int iy = 2 * y + tap / 7 - pad_t, ix = 2 * x + tap % 7 - pad_l;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+        v = __ldg(img + (((size_t)n * H + iy) * W + ix) * 3 + c);
+        if (image_norm) v = __fsub_rn(__fmul_rn(2.0f, __fdiv_rn(v, 255.0f)), 1.0f);
+      }
+    }
+    __half hh, ll;
+    split_f16(v, hh, ll);
+    hi[i] = hh;
+    lo[i] = ll;
+  }
+}
+
+// Folded inference BatchNorm: scale = gamma * rsqrt(var + eps), shift = beta - mean * scale.
+__global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const float* __restrict__ mean, const float* __restrict__ var, float eps, int C,
+                               float* __restrict__ scale, float* __restrict__ shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float s = gamma[c] * rsqrtf(var[c] + eps);
+  scale[c] = s;
+  shift[c] = beta[c] - mean[c] * s;
+}
+// tanh / relu split of the context encoder output (model.py:84-86): (npix, hid+ctx) -> net (npix, hid), inp (npix, ctx)
+__global__ void context_split_kernel(const float* __restrict__ cnet, size_t npix, int hid, int ctx,
+                                     float* __restrict__ net, float* __restrict__ inp) {
+  const int C = hid + ctx;
+  const size_t total = npix * (size_t)C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t px = i / C;
+    const int c = (int)(i - px * C);
+    const float v = cnet[i];
+    if (c < hid) net[px * hid + c] = tanhf(v);
+    else inp[px * ctx + (c - hid)] = fmaxf(v, 0.f);
   }
 }
 

@@ -27,7 +27,7 @@ inline EncodeTiledFn encode_tiled_fn() {
 // fp16 tensor, innermost dim contiguous, 128-byte swizzle, zero fill out of bounds.
 // dims/box innermost-first; strides_bytes has rank-1 entries (dims 1..rank-1).
 inline int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                         const uint64_t* strides_bytes, const uint32_t* box) {
+                         const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides = nullptr) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return RAFT_ERR_DRIVER;
   cuuint64_t gdim[5], gstr[4];
@@ -35,7 +35,7 @@ inline int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uin
   for (int i = 0; i < rank; ++i) {
     gdim[i] = dims[i];
     bx[i] = box[i];
-    es[i] = 1;
+    es[i] = elem_strides ? elem_strides[i] : 1;
     if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
   }
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx,
@@ -45,11 +45,16 @@ inline int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uin
 }
 
 // NHWC fp16 activation plane [B][H][W][cstride] -> rank-4 map, box {64 ch, tw, th, 1}.
-inline int make_tmap_act(CUtensorMap* out, const __half* base, int B, int H, int W, int cstride, int tw, int th) {
+// `stride` > 1 samples every stride-th pixel (TMA elementStrides): the box spans tw*stride x th*stride input
+// pixels and delivers tw x th of them -- the A operand of a strided convolution, still one TMA per tap.
+inline int make_tmap_act(CUtensorMap* out, const __half* base, int B, int H, int W, int cstride, int tw, int th,
+                         int stride = 1) {
   uint64_t dims[4] = {(uint64_t)cstride, (uint64_t)W, (uint64_t)H, (uint64_t)B};
   uint64_t str[3] = {(uint64_t)cstride * 2, (uint64_t)W * cstride * 2, (uint64_t)H * W * cstride * 2};
-  uint32_t box[4] = {64, (uint32_t)tw, (uint32_t)th, 1};
-  return make_tmap_f16(out, base, 4, dims, str, box);
+  uint32_t box[4] = {64, (uint32_t)(tw * stride), (uint32_t)(th * stride), 1};
+  uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+  if (tw * stride > 256 || th * stride > 256) return RAFT_ERR_BAD_SHAPE;
+  return make_tmap_f16(out, base, 4, dims, str, box, es);
 }
 
 // Packed weights [taps][cout_pad][cin_pad] fp16 -> rank-3 map, box {64 ch, bn, 1}.

@@ -1,15 +1,21 @@
-"""Feature / context encoders -- host-side mirror of tf_raft/layers/extractor.py.
+"""Feature / context encoders -- host-side mirror of tf_raft/layers/extractor.py (SURVEY.md 8(f) rank 1).
 
-SURVEY.md section 8(f) rank 1 ("next" row): the encoders run once per pair and are not yet hand-written
-kernels; they run as fp32 cuDNN convolutions through PyTorch (TF32 disabled) with the reference's
-TensorFlow semantics restated exactly: Keras 'same' padding (asymmetric for stride 2), tfa
-InstanceNormalization / Keras BatchNormalization with eps = 1e-3, NHWC tensors at the interface.
-Parameter names are the reference's Keras attribute paths, kernels HWIO.
+backend='native' (default): one call into libraft_b200.so (raft_b200_encoder_forward): every convolution on
+the tcgen05 kernel, stride-2 convolutions via TMA elementStrides, norms as fused epilogues (BatchNorm in
+inference) or deterministic reduction kernels (InstanceNorm).
+backend='torch': IEEE-fp32 cuDNN convolutions through PyTorch with the reference's TensorFlow semantics
+restated (Keras 'same' padding incl. the asymmetric stride-2 case, eps = 1e-3 norms) -- kept as an
+independent GPU cross-check of the native path, never selected implicitly.
+Parameter names are the reference's Keras attribute paths, kernels HWIO, NHWC tensors at the interface.
 """
+import ctypes
 import math
+import os
 
 import torch
 import torch.nn.functional as F
+
+from .. import _lib
 
 
 def force_ieee_fp32():
@@ -118,8 +124,14 @@ class _Encoder:
     """Common body of BasicEncoder / SmallEncoder (reference extractor.py:88-175)."""
     _c0 = 0
     _stages = ()
+    _variant = None
 
-    def __init__(self, output_dim=128, norm_type='batch', drop_rate=0.0, *, device='cuda', seed=None):
+    def __init__(self, output_dim=128, norm_type='batch', drop_rate=0.0, *, device='cuda', seed=None, backend=None):
+        self.backend = backend or os.environ.get('RAFT_B200_ENCODER', 'native')
+        if self.backend not in ('native', 'torch'):
+            raise ValueError(f'unknown encoder backend {self.backend!r}')
+        self._prepared = None
+        self._ws = {}
         self.output_dim = output_dim
         self.norm_type = Normalization(norm_type)
         self.drop_rate = drop_rate
@@ -149,9 +161,74 @@ class _Encoder:
 
     def load_params(self, params, prefix=''):
         self.store.load(params, prefix)
+        self._prepared = None
 
     def state_dict(self, prefix=''):
         return {prefix + k: v for k, v in self.store.params.items()}
+
+    # -- native path --------------------------------------------------------------------------------
+    def _conv_struct(self, name):
+        k = self.store.params[name + '.kernel']
+        return _lib.RaftConv(k.data_ptr(), self.store.params[name + '.bias'].data_ptr(), *k.shape)
+
+    def _norm_struct(self, name):
+        p = self.store.params
+        if self.norm_type is None:
+            return _lib.RaftNorm(None, None, None, None)
+        mm = p.get(name + '.moving_mean')
+        mv = p.get(name + '.moving_variance')
+        return _lib.RaftNorm(p[name + '.gamma'].data_ptr(), p[name + '.beta'].data_ptr(),
+                             None if mm is None else mm.data_ptr(), None if mv is None else mv.data_ptr())
+
+    def prepared(self):
+        if self._prepared is None:
+            L = _lib.lib()
+            w = _lib.RaftEncoderWeights()
+            w.conv1 = self._conv_struct('conv1')
+            w.norm1 = self._norm_struct('norm1')
+            k = 0
+            for li, (_, stride) in enumerate(self._stages, start=1):
+                for bi, st in enumerate((stride, 1)):
+                    p = f'layer{li}.{bi}'
+                    blk = w.block[k]
+                    blk.conv1, blk.conv2 = self._conv_struct(p + '.conv1'), self._conv_struct(p + '.conv2')
+                    blk.norm1, blk.norm2 = self._norm_struct(p + '.norm1'), self._norm_struct(p + '.norm2')
+                    if st != 1:
+                        blk.downsample = self._conv_struct(p + '.downsample.0')
+                        blk.downsample_norm = self._norm_struct(p + '.downsample.1')
+                    k += 1
+            w.conv2 = self._conv_struct('conv2')
+            nbytes = ctypes.c_size_t()
+            _lib.check(L.raft_b200_encoder_prepared_bytes(self._variant, self.output_dim, ctypes.byref(nbytes)),
+                       'encoder_prepared_bytes')
+            blob = _lib.workspace(nbytes.value, self.store.device)
+            with torch.cuda.device(self.store.device):
+                _lib.check(L.raft_b200_encoder_prepare(self._variant, _lib.NORM_TYPES[self.norm_type], self.output_dim,
+                                                       ctypes.cast(ctypes.pointer(w), ctypes.c_void_p), _lib.ptr(blob),
+                                                       blob.numel(), _lib.stream()), 'encoder_prepare')
+            self._prepared = blob
+        return self._prepared
+
+    def _native(self, x, training, raw_image):
+        x = _lib.f32c(x)
+        n, h, w, c = x.shape
+        if c != 3:
+            raise ValueError(f'encoder input must be (N, H, W, 3); got {tuple(x.shape)}')
+        L = _lib.lib()
+        key = (n, h, w)
+        if key not in self._ws:
+            nbytes = ctypes.c_size_t()
+            _lib.check(L.raft_b200_encoder_workspace_bytes(self._variant, n, h, w, ctypes.byref(nbytes)),
+                       'encoder_workspace_bytes')
+            self._ws = {key: _lib.workspace(nbytes.value, x.device)}
+        ws = self._ws[key]
+        out = torch.empty((n, -(-h // 8), -(-w // 8), self.output_dim), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(L.raft_b200_encoder_forward(self._variant, _lib.NORM_TYPES[self.norm_type], self.output_dim,
+                                                   _lib.ptr(self.prepared()), _lib.ptr(x), n, h, w, int(bool(training)),
+                                                   int(bool(raw_image)), _lib.ptr(out), _lib.ptr(ws), ws.numel(),
+                                                   _lib.stream()), 'encoder_forward')
+        return out
 
     def _res_block(self, x, p, stride, training):
         """Reference ResBlock.call, extractor.py:41-49."""
@@ -162,10 +239,21 @@ class _Encoder:
             x = s.norm(s.conv(x, p + '.downsample.0', stride, padding='valid'), p + '.downsample.1', nt, training)
         return F.relu(x + fx)
 
-    def __call__(self, inputs, training=False):
-        """NHWC tensor, or a list/tuple of two (concatenated along the batch, split on return)."""
+    def __call__(self, inputs, training=False, *, raw_image=False):
+        """NHWC tensor, or a list/tuple of two (concatenated along the batch, split on return).
+
+        `raw_image=True` (keyword-only extra): inputs are 0..255 images and the 2*(x/255)-1 of model.py:70-71
+        is applied inside (fused into the first load on the native path)."""
         is_list = isinstance(inputs, (tuple, list))
         x = torch.cat(list(inputs), dim=0) if is_list else inputs
+        if self.backend == 'native' and not (self.drop_rate > 0 and training):
+            out = self._native(x, training, raw_image)
+            if is_list:
+                n = out.shape[0] // 2
+                return [out[:n], out[n:]]
+            return out
+        if raw_image:
+            x = 2 * (x / 255.0) - 1.0
         x = x.permute(0, 3, 1, 2)
         s, nt = self.store, self.norm_type
         x = F.relu(s.norm(s.conv(x, 'conv1', 2), 'norm1', nt, training))
@@ -186,9 +274,11 @@ class BasicEncoder(_Encoder):
     """Reference extractor.py:88-130."""
     _c0 = 64
     _stages = ((64, 1), (96, 2), (128, 2))
+    _variant = _lib.VARIANT_BASIC
 
 
 class SmallEncoder(_Encoder):
     """Reference extractor.py:133-175 (built from ResBlocks, not bottlenecks)."""
     _c0 = 32
     _stages = ((32, 1), (64, 2), (96, 2))
+    _variant = _lib.VARIANT_SMALL

@@ -23,7 +23,7 @@ class RAFT:
     _variant = _lib.VARIANT_BASIC
 
     def __init__(self, drop_rate=0, iters=12, iters_pred=24, *, precision=None, device='cuda', seed=None,
-                 use_graph=False, **kwargs):
+                 use_graph=False, encoder_backend=None, **kwargs):
         self.hidden_dim = 128
         self.context_dim = 128
         self.corr_levels = 4
@@ -34,16 +34,21 @@ class RAFT:
         self.precision = _lib.resolve_precision(precision)
         self.device = torch.device(device)
         self.use_graph = use_graph
+        self.encoder_backend = encoder_backend
         self._build_layers(seed)
         self._graphs = {}
         self.flow_metrics = None
 
+    def _encoder_backend(self):
+        # the all-FFMA reference configuration keeps cuDNN IEEE-fp32 encoders; the product path is native
+        return self.encoder_backend or ('native' if self.precision == _lib.PREC_F16X2 else 'torch')
+
     def _build_layers(self, seed):
         s = 0 if seed is None else seed
         self.fnet = BasicEncoder(output_dim=256, norm_type='instance', drop_rate=self.drop_rate, device=self.device,
-                                 seed=s)
+                                 seed=s, backend=self._encoder_backend())
         self.cnet = BasicEncoder(output_dim=self.hidden_dim + self.context_dim, norm_type='batch',
-                                 drop_rate=self.drop_rate, device=self.device, seed=s + 1)
+                                 drop_rate=self.drop_rate, device=self.device, seed=s + 1, backend=self._encoder_backend())
         self.update_block = BasicUpdateBlock(filters=self.hidden_dim, precision=self.precision, device=self.device,
                                              seed=s + 2)
 
@@ -82,12 +87,16 @@ class RAFT:
 
     # -- forward ----------------------------------------------------------------------------------
     def _encode(self, image1, image2, training):
-        image1 = 2 * (image1 / 255.0) - 1.0                                   # model.py:70-71
-        image2 = 2 * (image2 / 255.0) - 1.0
-        fmap1, fmap2 = self.fnet([image1, image2], training=training)         # :74
-        cnet = self.cnet(image1, training=training)                           # :82
-        net = torch.tanh(cnet[..., :self.hidden_dim]).contiguous()            # :84-86
-        inp = F.relu(cnet[..., self.hidden_dim:]).contiguous()
+        # model.py:70-71 (2*(x/255)-1) happens inside the encoders' first load (raw_image=True)
+        fmap1, fmap2 = self.fnet([image1, image2], training=training, raw_image=True)     # :74
+        cnet = self.cnet(image1, training=training, raw_image=True)                       # :82
+        b, h, w, _ = cnet.shape
+        net = torch.empty((b, h, w, self.hidden_dim), dtype=torch.float32, device=cnet.device)
+        inp = torch.empty((b, h, w, self.context_dim), dtype=torch.float32, device=cnet.device)
+        with torch.cuda.device(cnet.device):                                              # :84-86
+            _lib.check(_lib.lib().raft_b200_context_split(_lib.ptr(cnet), b * h * w, self.hidden_dim,
+                                                          self.context_dim, _lib.ptr(net), _lib.ptr(inp),
+                                                          _lib.stream()), 'context_split')
         return fmap1, fmap2, net, inp
 
     def _loop(self, corr_block, net, inp, coords1, flow_ups, b, h, w):
@@ -178,9 +187,9 @@ class SmallRAFT(RAFT):
         self.corr_radius = 3
         s = 0 if seed is None else seed
         self.fnet = SmallEncoder(output_dim=128, norm_type='instance', drop_rate=self.drop_rate, device=self.device,
-                                 seed=s)
+                                 seed=s, backend=self._encoder_backend())
         self.cnet = SmallEncoder(output_dim=self.hidden_dim + self.context_dim, norm_type=None,
-                                 drop_rate=self.drop_rate, device=self.device, seed=s + 1)
+                                 drop_rate=self.drop_rate, device=self.device, seed=s + 1, backend=self._encoder_backend())
         self.update_block = SmallUpdateBlock(filters=self.hidden_dim, precision=self.precision, device=self.device,
                                              seed=s + 2)
 

@@ -215,11 +215,14 @@ static int update_core_tc(const UpdateCtx& c, float* h, float* delta, float* mas
       TcSeg s[1] = {{W.cor1_hi, W.cor1_lo, d.s_cor1, 0, 4}};
       RAFT_TRY(launch_tc_layer(c, 1, 1, s, p));
     }
-    // convf1 7x7 2->128 + relu: K = 98, a CUDA-core job; writes the fp16 planes directly
-    {
-      const float* s[1] = {W.flow};
-      int st[1] = {2}, o[1] = {0}, n[1] = {2};
-      RAFT_TRY(launch_simt_conv(c, BF1, 1, s, st, o, n, nullptr, 0, 0, SACT_RELU, 1.0f, W.flo1_hi, W.flo1_lo, d.s_flo1, 0));
+    {  // convf1 7x7 2->128 + relu: K = 98 -> gather the window into 128-channel planes, run as a 1x1 GEMM
+      const size_t npix = (size_t)c.B * c.h * c.w;
+      flow_im2col_kernel<<<grid_for(npix * 128), 256, 0, c.stream>>>(W.flow, c.B, c.h, c.w, W.fim_hi, W.fim_lo);
+      RAFT_COUNT_LAUNCH();
+      tc_params_init(p, EPI_LINEAR, ACT_RELU, 128);
+      p.out_hi = W.flo1_hi; p.out_lo = W.flo1_lo; p.h_stride = d.s_flo1;
+      TcSeg s[1] = {{W.fim_hi, W.fim_lo, 128, 0, 2}};
+      RAFT_TRY(launch_tc_layer(c, 11, 1, s, p));
     }
     {  // convf2 3x3 128->64 + relu -> cor_flo[192:256)
       tc_params_init(p, EPI_LINEAR, ACT_RELU, 64);
@@ -261,10 +264,14 @@ static int update_core_tc(const UpdateCtx& c, float* h, float* delta, float* mas
       TcSeg s[1] = {{W.corr_hi, W.corr_lo, d.s_corr, 0, 4}};
       RAFT_TRY(launch_tc_layer(c, 0, 1, s, p));
     }
-    {
-      const float* s[1] = {W.flow};
-      int st[1] = {2}, o[1] = {0}, n[1] = {2};
-      RAFT_TRY(launch_simt_conv(c, SF1, 1, s, st, o, n, nullptr, 0, 0, SACT_RELU, 1.0f, W.flo1_hi, W.flo1_lo, d.s_flo1, 0));
+    {  // convf1 7x7 2->64 + relu via im2col + 1x1 GEMM
+      const size_t npix = (size_t)c.B * c.h * c.w;
+      flow_im2col_kernel<<<grid_for(npix * 128), 256, 0, c.stream>>>(W.flow, c.B, c.h, c.w, W.fim_hi, W.fim_lo);
+      RAFT_COUNT_LAUNCH();
+      tc_params_init(p, EPI_LINEAR, ACT_RELU, 64);
+      p.out_hi = W.flo1_hi; p.out_lo = W.flo1_lo; p.h_stride = d.s_flo1;
+      TcSeg s[1] = {{W.fim_hi, W.fim_lo, 128, 0, 2}};
+      RAFT_TRY(launch_tc_layer(c, 7, 1, s, p));
     }
     {  // convf2 3x3 64->32 + relu -> cor_flo[96:128)
       tc_params_init(p, EPI_LINEAR, ACT_RELU, 32);
@@ -532,6 +539,7 @@ int raft_b200_update_prepare(int variant, const void* weights, void* prepared, s
         memset(&pp, 0, sizeof(pp));
         pp.w = convs[ci].kernel;
         pp.kh = cd[ci].kh; pp.kw = cd[ci].kw; pp.cin = cd[ci].cin; pp.cout = cd[ci].cout;
+        if (T.flatten) { pp.cin = pp.kh * pp.kw * pp.cin; pp.kh = pp.kw = 1; }   // HWIO is already [tap*cin + c][cout]
         pp.hi = reinterpret_cast<__half*>(base + L.tc_hi[li]);
         pp.lo = reinterpret_cast<__half*>(base + L.tc_lo[li]);
         pp.cout_pad = T.cout_pad; pp.cin_pad = T.cin_pad; pp.cout_off = cout_off;

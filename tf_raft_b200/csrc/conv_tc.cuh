@@ -67,31 +67,119 @@ struct alignas(64) TcConvParams {
 };
 
 #if defined(__CUDA_ARCH__)
-__device__ __forceinline__ void store_f32x32(float* dst, const float (&v)[32], int nvalid, bool vec_ok) {
-  if (nvalid >= 32 && vec_ok) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-  } else {
-#pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (j < nvalid) dst[j] = v[j];
+// ------------------------------------------------------------------------------------------------
+// Epilogue of one 32-column chunk of one pixel row.  Deliberately NOT inlined and written as rolled
+// loops over 4-element groups on a local-memory buffer: the fully unrolled multi-mode version was
+// 384 KB of SASS and instruction fetch ("no_instructions") became the top stall of every short-K layer.
+//   v[32]  accumulator values (in), pix = pixel index, col = first global output column, ncol = 32|16
+// ------------------------------------------------------------------------------------------------
+__device__ __noinline__ void tc_epilogue_chunk(const TcConvParams& p, float* v, size_t pix, int col, int ncol,
+                                               float inv_scale) {
+  if (p.mode == EPI_CORR) {
+    const int nvalid = min(ncol, p.n_total - col);
+    if (nvalid <= 0) return;
+    float* dst = p.out_f32 + pix * (size_t)p.f32_stride + col;
+    if (nvalid == 32 && (p.f32_stride & 3) == 0) {
+#pragma unroll 1
+      for (int q = 0; q < 8; ++q)
+        reinterpret_cast<float4*>(dst)[q] = make_float4(__fdiv_rn(v[4 * q], p.corr_div), __fdiv_rn(v[4 * q + 1], p.corr_div),
+                                                        __fdiv_rn(v[4 * q + 2], p.corr_div), __fdiv_rn(v[4 * q + 3], p.corr_div));
+    } else {
+#pragma unroll 1
+      for (int j = 0; j < nvalid; ++j) dst[j] = __fdiv_rn(v[j], p.corr_div);
+    }
+    return;
   }
-}
-__device__ __forceinline__ void store_split32(__half* dhi, __half* dlo, const float (&v)[32]) {
-  uint32_t ph[16], pl[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    __half h0, l0, h1, l1;
-    split_f16(v[2 * j], h0, l0);
-    split_f16(v[2 * j + 1], h1, l1);
-    ph[j] = pack_h2(h0, h1);
-    pl[j] = pack_h2(l0, l1);
+
+  // bias (+ folded BatchNorm affine)
+#pragma unroll 1
+  for (int j = 0; j < 32; ++j) {
+    float t = v[j] * inv_scale;
+    if (p.bias) t += __ldg(p.bias + col + j);
+    if (p.post_scale) t = t * __ldg(p.post_scale + col + j) + __ldg(p.post_shift + col + j);
+    v[j] = t;
   }
+
+  __half* dhi = nullptr;
+  __half* dlo = nullptr;
+  if (p.mode == EPI_LINEAR) {
+    const float* res = p.residual ? p.residual + pix * (size_t)p.res_stride + p.res_c0 + col : nullptr;
+#pragma unroll 1
+    for (int j = 0; j < 32; ++j) {
+      float t = v[j];
+      if (p.act == ACT_RELU) t = fmaxf(t, 0.0f);
+      t *= p.out_scale;
+      if (col + j >= p.n_total) {                  // padded columns: concat tail, else exact zeros
+        const int cj = col + j - p.n_total;
+        t = (p.concat_src && cj < p.concat_n) ? __ldg(p.concat_src + pix * p.concat_n + cj) : 0.0f;
+      } else if (res) {
+        t = fmaxf(t + __ldg(res + j), 0.0f);
+      }
+      v[j] = t;
+    }
+    if (p.out_f32) {
+      const int nvalid = min(ncol, p.n_total - col);
+      float* dst = p.out_f32 + pix * (size_t)p.f32_stride + p.f32_c0 + col;
+      if (nvalid == 32 && ((p.f32_stride | p.f32_c0) & 3) == 0) {
+#pragma unroll 1
+        for (int q = 0; q < 8; ++q)
+          reinterpret_cast<float4*>(dst)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      } else {
+#pragma unroll 1
+        for (int j = 0; j < nvalid; ++j) dst[j] = v[j];
+      }
+    }
+    if (p.out_hi && ncol == 32) {
+      const size_t o = pix * (size_t)p.h_stride + p.h_c0 + col;
+      dhi = p.out_hi + o;
+      dlo = p.out_lo + o;
+    }
+  } else if (p.mode == EPI_GRU_ZR) {
+    if (col < p.hid) {                              // z gate -> fp32 plane
+      float* dst = p.z + pix * (size_t)p.hid + col;
+#pragma unroll 1
+      for (int q = 0; q < 8; ++q)
+        reinterpret_cast<float4*>(dst)[q] = make_float4(sigmoidf_acc(v[4 * q]), sigmoidf_acc(v[4 * q + 1]),
+                                                        sigmoidf_acc(v[4 * q + 2]), sigmoidf_acc(v[4 * q + 3]));
+    } else {                                        // r gate -> r*h, re-split for the q convolution
+      const int hc = col - p.hid;
+      const float* hp = p.h + pix * (size_t)p.hid + hc;
+#pragma unroll 1
+      for (int j = 0; j < 32; ++j) v[j] = sigmoidf_acc(v[j]) * __ldg(hp + j);
+      const size_t o = pix * (size_t)p.h_stride + p.h_c0 + hc;
+      dhi = p.out_hi + o;
+      dlo = p.out_lo + o;
+    }
+  } else {                                          // EPI_GRU_Q: h = (1-z)*h + z*tanh(v), in place
+    float* hrow = p.h + pix * (size_t)p.hid + col;
+    const float* zp = p.z + pix * (size_t)p.hid + col;
+#pragma unroll 1
+    for (int j = 0; j < 32; ++j) {
+      const float zv = __ldg(zp + j);
+      const float hn = (1.0f - zv) * hrow[j] + zv * tanhf(v[j]);
+      v[j] = hn;
+      hrow[j] = hn;
+    }
+    const size_t o = pix * (size_t)p.h_stride + p.h_c0 + col;
+    dhi = p.out_hi + o;
+    dlo = p.out_lo + o;
+  }
+
+  if (dhi) {                                        // fp16 hi/lo re-split, 8 channels (16 bytes) per store
+#pragma unroll 1
+    for (int q = 0; q < 4; ++q) {
+      uint32_t ph[4], pl[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    reinterpret_cast<uint4*>(dhi)[j] = make_uint4(ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
-    reinterpret_cast<uint4*>(dlo)[j] = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+      for (int e = 0; e < 4; ++e) {
+        __half h0, l0, h1, l1;
+        split_f16(v[8 * q + 2 * e], h0, l0);
+        split_f16(v[8 * q + 2 * e + 1], h1, l1);
+        ph[e] = pack_h2(h0, h1);
+        pl[e] = pack_h2(l0, l1);
+      }
+      reinterpret_cast<uint4*>(dhi)[q] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+      reinterpret_cast<uint4*>(dlo)[q] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+    }
   }
 }
 #endif
@@ -264,93 +352,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       }
     }
 
+    if (valid) {
+      float buf[32];
 #pragma unroll
-    for (int ci = 0; ci < 4; ++ci) {
-      if (ci >= my_chunks) continue;
-      const int c0 = (chunk0 + ci) * 32;
-      const int ncol = min(32, p.bn - c0);           // bn is a multiple of 16: 32 or 16
-      if (!valid) continue;
-      const int col = n0 + c0;                       // first global output column of this chunk
-      float v[32];
-
-      if (p.mode == EPI_CORR) {
+      for (int ci = 0; ci < 4; ++ci) {
+        if (ci < my_chunks) {
+          const int c0 = (chunk0 + ci) * 32;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __fdiv_rn(racc[ci][j], p.corr_div);
-        const int nvalid = min(ncol, p.n_total - col);
-        if (nvalid > 0) {
-          float* dst = p.out_f32 + pix * (size_t)p.f32_stride + col;
-          store_f32x32(dst, v, nvalid, (p.f32_stride & 3) == 0);
+          for (int j = 0; j < 32; ++j) buf[j] = racc[ci][j];
+          tc_epilogue_chunk(p, buf, pix, n0 + c0, min(32, p.bn - c0), inv_scale);
         }
-        continue;
-      }
-
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float t = racc[ci][j] * inv_scale;
-        if (p.bias) t += __ldg(p.bias + col + j);
-        if (p.post_scale) t = t * __ldg(p.post_scale + col + j) + __ldg(p.post_shift + col + j);
-        v[j] = t;
-      }
-
-      if (p.mode == EPI_LINEAR) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float t = v[j];
-          if (p.act == ACT_RELU) t = fmaxf(t, 0.0f);
-          t *= p.out_scale;
-          if (p.residual && col + j < p.n_total)
-            t = fmaxf(t + __ldg(p.residual + pix * (size_t)p.res_stride + p.res_c0 + col + j), 0.0f);
-          if (col + j >= p.n_total) {                // padded columns: concat tail, else exact zeros
-            const int cj = col + j - p.n_total;
-            t = (p.concat_src && cj < p.concat_n) ? __ldg(p.concat_src + pix * p.concat_n + cj) : 0.0f;
-          }
-          v[j] = t;
-        }
-        if (p.out_f32) {
-          const int nvalid = min(ncol, p.n_total - col);
-          if (nvalid > 0)
-            store_f32x32(p.out_f32 + pix * (size_t)p.f32_stride + p.f32_c0 + col, v, nvalid,
-                         ((p.f32_stride | p.f32_c0) & 3) == 0);
-        }
-        if (p.out_hi) {
-          const size_t o = pix * (size_t)p.h_stride + p.h_c0 + col;
-          store_split32(p.out_hi + o, p.out_lo + o, v);
-        }
-      } else if (p.mode == EPI_GRU_ZR) {
-        if (col < p.hid) {                            // z gate
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = sigmoidf_acc(v[j]);
-          store_f32x32(p.z + pix * (size_t)p.hid + col, v, 32, true);
-        } else {                                      // r gate -> r*h, re-split for the q convolution
-          const int hc = col - p.hid;
-          const float4* hp = reinterpret_cast<const float4*>(p.h + pix * (size_t)p.hid + hc);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 hv = __ldg(hp + j);
-            v[4 * j] = sigmoidf_acc(v[4 * j]) * hv.x;
-            v[4 * j + 1] = sigmoidf_acc(v[4 * j + 1]) * hv.y;
-            v[4 * j + 2] = sigmoidf_acc(v[4 * j + 2]) * hv.z;
-            v[4 * j + 3] = sigmoidf_acc(v[4 * j + 3]) * hv.w;
-          }
-          const size_t o = pix * (size_t)p.h_stride + p.h_c0 + hc;
-          store_split32(p.out_hi + o, p.out_lo + o, v);
-        }
-      } else {  // EPI_GRU_Q
-        float* hrow = p.h + pix * (size_t)p.hid + col;
-        const float4* hp = reinterpret_cast<const float4*>(hrow);
-        const float4* zp = reinterpret_cast<const float4*>(p.z + pix * (size_t)p.hid + col);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 hv = hp[j];
-          const float4 zv = __ldg(zp + j);
-          v[4 * j] = (1.0f - zv.x) * hv.x + zv.x * tanhf(v[4 * j]);
-          v[4 * j + 1] = (1.0f - zv.y) * hv.y + zv.y * tanhf(v[4 * j + 1]);
-          v[4 * j + 2] = (1.0f - zv.z) * hv.z + zv.z * tanhf(v[4 * j + 2]);
-          v[4 * j + 3] = (1.0f - zv.w) * hv.w + zv.w * tanhf(v[4 * j + 3]);
-        }
-        store_f32x32(hrow, v, 32, true);
-        const size_t o = pix * (size_t)p.h_stride + p.h_c0 + col;
-        store_split32(p.out_hi + o, p.out_lo + o, v);
       }
     }
   }

@@ -556,6 +556,28 @@ __global__ void stem_im2col_kernel(const float* __restrict__ img, int N, int H, 
   }
 }
 
+// im2col of the 7x7 'same' window of the 2-channel flow (update.py:92,75: convf1), tap-major then (x, y) channel:
+// 98 values per pixel, zero outside the image, as fp16 hi/lo planes of 128 channels (98..127 = 0).
+__global__ void flow_im2col_kernel(const float* __restrict__ flow, int B, int h, int w, __half* __restrict__ hi,
+                                   __half* __restrict__ lo) {
+  const size_t total = (size_t)B * h * w * 128;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int kk = (int)(i & 127);
+    const size_t px = i >> 7;
+    float v = 0.f;
+    if (kk < 98) {
+      const int x = (int)(px % w), y = (int)((px / w) % h);
+      const int tap = kk >> 1, c = kk & 1;
+      const int yy = y + tap / 7 - 3, xx = x + tap % 7 - 3;
+      if (yy >= 0 && yy < h && xx >= 0 && xx < w) v = __ldg(flow + (px + (size_t)(yy - y) * w + (xx - x)) * 2 + c);
+    }
+    __half hh, ll;
+    split_f16(v, hh, ll);
+    hi[i] = hh;
+    lo[i] = ll;
+  }
+}
+
 // Folded inference BatchNorm: scale = gamma * rsqrt(var + eps), shift = beta - mean * scale.
 __global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
                                const float* __restrict__ mean, const float* __restrict__ var, float eps, int C,

@@ -43,9 +43,10 @@ struct TcLayerSpec {
   int cin_pad, cout_pad;       // packed dims
   int nrange, r_src0[2], r_n[2], r_dst0[2];   // cin remap
   int bn, ntn;                 // N per CTA, N tiles
+  int flatten;                 // 1: (kh,kw,cin) flattened into the channel axis -- the layer runs as a 1x1 conv on im2col planes
 };
 
-static const TcLayerSpec kBasicTc[11] = {
+static const TcLayerSpec kBasicTc[12] = {
     /*T0 convc1 */ {1, {BC1, -1}, 1, 1, 384, 256, 1, {0, 0}, {324, 0}, {0, 0}, 256, 1},
     /*T1 convc2 */ {1, {BC2, -1}, 3, 3, 256, 192, 1, {0, 0}, {256, 0}, {0, 0}, 192, 1},
     /*T2 convf2 */ {1, {BF2, -1}, 3, 3, 128, 64, 1, {0, 0}, {128, 0}, {0, 0}, 64, 1},
@@ -56,18 +57,20 @@ static const TcLayerSpec kBasicTc[11] = {
     /*T7 q2     */ {1, {BQ2, -1}, 5, 1, 384, 128, 1, {0, 0}, {384, 0}, {0, 0}, 128, 1},
     /*T8 fh1|m0 */ {2, {BFH1, BM0}, 3, 3, 128, 512, 1, {0, 0}, {128, 0}, {0, 0}, 256, 2},
     /*T9 fh2    */ {1, {BFH2, -1}, 3, 3, 256, 16, 1, {0, 0}, {256, 0}, {0, 0}, 16, 1},
-    /*T10 mask2 */ {1, {BM2, -1}, 1, 1, 256, 576, 1, {0, 0}, {256, 0}, {0, 0}, 192, 3}};
+    /*T10 mask2 */ {1, {BM2, -1}, 1, 1, 256, 576, 1, {0, 0}, {256, 0}, {0, 0}, 192, 3},
+    /*T11 convf1*/ {1, {BF1, -1}, 1, 1, 128, 128, 1, {0, 0}, {98, 0}, {0, 0}, 128, 1, 1}};
 
-static const TcLayerSpec kSmallTc[7] = {
+static const TcLayerSpec kSmallTc[8] = {
     /*S0 convc1 */ {1, {SC1, -1}, 1, 1, 256, 96, 1, {0, 0}, {196, 0}, {0, 0}, 96, 1},
     /*S1 convf2 */ {1, {SF2, -1}, 3, 3, 64, 32, 1, {0, 0}, {64, 0}, {0, 0}, 32, 1},
     /*S2 conv   */ {1, {SCV, -1}, 3, 3, 128, 96, 1, {0, 0}, {128, 0}, {0, 0}, 96, 1},
     /*S3 zr     */ {2, {SZ, SR}, 3, 3, 320, 192, 2, {0, 96}, {96, 146}, {0, 128}, 192, 1},
     /*S4 q      */ {1, {SQ, -1}, 3, 3, 320, 96, 2, {0, 96}, {96, 146}, {0, 128}, 96, 1},
     /*S5 fh1    */ {1, {SFH1, -1}, 3, 3, 128, 128, 1, {0, 0}, {96, 0}, {0, 0}, 128, 1},
-    /*S6 fh2    */ {1, {SFH2, -1}, 3, 3, 128, 16, 1, {0, 0}, {128, 0}, {0, 0}, 16, 1}};
+    /*S6 fh2    */ {1, {SFH2, -1}, 3, 3, 128, 16, 1, {0, 0}, {128, 0}, {0, 0}, 16, 1},
+    /*S7 convf1 */ {1, {SF1, -1}, 1, 1, 128, 64, 1, {0, 0}, {98, 0}, {0, 0}, 64, 1, 1}};
 
-inline int n_tc_layers(int variant) { return variant == RAFT_VARIANT_BASIC ? 11 : 7; }
+inline int n_tc_layers(int variant) { return variant == RAFT_VARIANT_BASIC ? 12 : 8; }
 inline const TcLayerSpec* tc_layers(int variant) { return variant == RAFT_VARIANT_BASIC ? kBasicTc : kSmallTc; }
 
 // ------------------------------------------------------------------------------------------------
@@ -75,7 +78,7 @@ inline const TcLayerSpec* tc_layers(int variant) { return variant == RAFT_VARIAN
 // ------------------------------------------------------------------------------------------------
 struct PreparedLayout {
   size_t raw_w[15], raw_b[15];                 // fp32 copies of every reference conv (HWIO) + bias
-  size_t tc_hi[11], tc_lo[11], tc_bias[11], tc_scale[11], tc_absmax[11];
+  size_t tc_hi[12], tc_lo[12], tc_bias[12], tc_scale[12], tc_absmax[12];
   size_t total;
 };
 
@@ -131,7 +134,7 @@ struct Workspace {
   float *corr, *cor1, *cf, *flo1, *x, *z, *r, *rh, *q, *fm, *flow, *delta, *mask, *net_tmp;
   // fp16 hi/lo planes (tensor-core path)
   __half *corr_hi, *corr_lo, *cor1_hi, *cor1_lo, *cf_hi, *cf_lo, *flo1_hi, *flo1_lo, *x_hi, *x_lo, *h_hi, *h_lo,
-      *rh_hi, *rh_lo, *fm_hi, *fm_lo;
+      *rh_hi, *rh_lo, *fm_hi, *fm_lo, *fim_hi, *fim_lo;
   uint8_t* f16_begin; size_t f16_bytes;
   size_t total;
 };
@@ -178,6 +181,7 @@ inline Workspace workspace_layout(void* base, int variant, int B, int h, int w, 
     W.h_hi = f16(d.s_h); W.h_lo = f16(d.s_h);
     W.rh_hi = f16(d.s_h); W.rh_lo = f16(d.s_h);
     W.fm_hi = f16(d.s_fm); W.fm_lo = f16(d.s_fm);
+    W.fim_hi = f16(128); W.fim_lo = f16(128);      // im2col of the 7x7 flow window (98 -> 128 channels)
     W.f16_bytes = (size_t)((b8 + off) - W.f16_begin);
   }
   W.total = off;

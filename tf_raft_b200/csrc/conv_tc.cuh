@@ -21,6 +21,8 @@
 //   GRU gating / hi-lo re-split -> global).  mbarrier rings: smem full/empty (producer <-> issuer),
 //   TMEM full/empty (issuer <-> promotion warps).
 #pragma once
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tmap.cuh"
 
@@ -48,8 +50,11 @@ struct alignas(64) TcConvParams {
   int stride;                     // 1 or 2: input pixel = output pixel * stride + tap - pad (TMA elementStrides)
   int B, H, W, TH, TW, tiles_x, tiles_y;
   int bn, n_total;                // N per CTA (multiple of 16, <= 256); total valid output columns
+  int n_tiles_n;                  // column tiles (tile id = n_tile * pixel_tiles + pixel_tile)
   int nstages, stage_bytes, tmem_cols;
   int group_chunks;               // K chunks per promotion group (accumulation chain = 12 * group_chunks MMAs)
+  int cluster;                    // CTAs per cluster along the pixel-tile axis (1, 2, 4): the weight tile is loaded
+                                  // once per cluster -- each CTA fetches bn/cluster rows and multicasts them
   int b_batch_stride;             // B-map coordinate 2 = tap + b * b_batch_stride (correlation: 1, taps = 1)
   int mode, act;
   const float* bias;              // [n_total padded to bn multiple]; may be null
@@ -73,17 +78,25 @@ struct alignas(64) TcConvParams {
 // 384 KB of SASS and instruction fetch ("no_instructions") became the top stall of every short-K layer.
 //   v[32]  accumulator values (in), pix = pixel index, col = first global output column, ncol = 32|16
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
 __device__ __noinline__ void tc_epilogue_chunk(const TcConvParams& p, float* v, size_t pix, int col, int ncol,
                                                float inv_scale) {
+  // All loops are rolled (#pragma unroll 1) over groups of 4 columns with 16-byte accesses: every row of the
+  // tile is owned by one thread, so vector width -- not coalescing across lanes -- sets the memory efficiency.
   if (p.mode == EPI_CORR) {
     const int nvalid = min(ncol, p.n_total - col);
     if (nvalid <= 0) return;
     float* dst = p.out_f32 + pix * (size_t)p.f32_stride + col;
     if (nvalid == 32 && (p.f32_stride & 3) == 0) {
 #pragma unroll 1
-      for (int q = 0; q < 8; ++q)
-        reinterpret_cast<float4*>(dst)[q] = make_float4(__fdiv_rn(v[4 * q], p.corr_div), __fdiv_rn(v[4 * q + 1], p.corr_div),
-                                                        __fdiv_rn(v[4 * q + 2], p.corr_div), __fdiv_rn(v[4 * q + 3], p.corr_div));
+      for (int q = 0; q < 8; ++q) {
+        const float4 a = ld4(v + 4 * q);
+        st4(dst + 4 * q, make_float4(__fdiv_rn(a.x, p.corr_div), __fdiv_rn(a.y, p.corr_div), __fdiv_rn(a.z, p.corr_div),
+                                     __fdiv_rn(a.w, p.corr_div)));
+      }
     } else {
 #pragma unroll 1
       for (int j = 0; j < nvalid; ++j) dst[j] = __fdiv_rn(v[j], p.corr_div);
@@ -91,39 +104,63 @@ __device__ __noinline__ void tc_epilogue_chunk(const TcConvParams& p, float* v, 
     return;
   }
 
-  // bias (+ folded BatchNorm affine)
+  // bias (+ folded BatchNorm affine); the bias / affine arrays are zero-padded past the last column
 #pragma unroll 1
-  for (int j = 0; j < 32; ++j) {
-    float t = v[j] * inv_scale;
-    if (p.bias) t += __ldg(p.bias + col + j);
-    if (p.post_scale) t = t * __ldg(p.post_scale + col + j) + __ldg(p.post_shift + col + j);
-    v[j] = t;
+  for (int q = 0; q < 8; ++q) {
+    float4 t = ld4(v + 4 * q);
+    t.x *= inv_scale; t.y *= inv_scale; t.z *= inv_scale; t.w *= inv_scale;
+    if (p.bias) {
+      const float4 b = ldg4(p.bias + col + 4 * q);
+      t.x += b.x; t.y += b.y; t.z += b.z; t.w += b.w;
+    }
+    if (p.post_scale) {
+      const float4 sc = ldg4(p.post_scale + col + 4 * q), sh = ldg4(p.post_shift + col + 4 * q);
+      t.x = t.x * sc.x + sh.x; t.y = t.y * sc.y + sh.y; t.z = t.z * sc.z + sh.z; t.w = t.w * sc.w + sh.w;
+    }
+    st4(v + 4 * q, t);
   }
 
   __half* dhi = nullptr;
   __half* dlo = nullptr;
   if (p.mode == EPI_LINEAR) {
-    const float* res = p.residual ? p.residual + pix * (size_t)p.res_stride + p.res_c0 + col : nullptr;
+    const bool full = col + 32 <= p.n_total;       // chunk entirely inside the valid columns (the common case)
+    if (full) {
+      const float* res = p.residual ? p.residual + pix * (size_t)p.res_stride + p.res_c0 + col : nullptr;
+      const bool res_vec = ((p.res_stride | p.res_c0) & 3) == 0;
 #pragma unroll 1
-    for (int j = 0; j < 32; ++j) {
-      float t = v[j];
-      if (p.act == ACT_RELU) t = fmaxf(t, 0.0f);
-      t *= p.out_scale;
-      if (col + j >= p.n_total) {                  // padded columns: concat tail, else exact zeros
-        const int cj = col + j - p.n_total;
-        t = (p.concat_src && cj < p.concat_n) ? __ldg(p.concat_src + pix * p.concat_n + cj) : 0.0f;
-      } else if (res) {
-        t = fmaxf(t + __ldg(res + j), 0.0f);
+      for (int q = 0; q < 8; ++q) {
+        float4 t = ld4(v + 4 * q);
+        if (p.act == ACT_RELU) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
+        t.x *= p.out_scale; t.y *= p.out_scale; t.z *= p.out_scale; t.w *= p.out_scale;
+        if (res) {
+          float4 r;
+          if (res_vec) r = ldg4(res + 4 * q);
+          else r = make_float4(__ldg(res + 4 * q), __ldg(res + 4 * q + 1), __ldg(res + 4 * q + 2), __ldg(res + 4 * q + 3));
+          t.x = fmaxf(t.x + r.x, 0.f); t.y = fmaxf(t.y + r.y, 0.f); t.z = fmaxf(t.z + r.z, 0.f); t.w = fmaxf(t.w + r.w, 0.f);
+        }
+        st4(v + 4 * q, t);
       }
-      v[j] = t;
+    } else {
+#pragma unroll 1
+      for (int j = 0; j < 32; ++j) {
+        float t = v[j];
+        if (p.act == ACT_RELU) t = fmaxf(t, 0.0f);
+        t *= p.out_scale;
+        if (col + j >= p.n_total) {                // padded columns: concat tail, else exact zeros
+          const int cj = col + j - p.n_total;
+          t = (p.concat_src && cj < p.concat_n) ? __ldg(p.concat_src + pix * p.concat_n + cj) : 0.0f;
+        } else if (p.residual) {
+          t = fmaxf(t + __ldg(p.residual + pix * (size_t)p.res_stride + p.res_c0 + col + j), 0.0f);
+        }
+        v[j] = t;
+      }
     }
     if (p.out_f32) {
       const int nvalid = min(ncol, p.n_total - col);
       float* dst = p.out_f32 + pix * (size_t)p.f32_stride + p.f32_c0 + col;
       if (nvalid == 32 && ((p.f32_stride | p.f32_c0) & 3) == 0) {
 #pragma unroll 1
-        for (int q = 0; q < 8; ++q)
-          reinterpret_cast<float4*>(dst)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        for (int q = 0; q < 8; ++q) st4(dst + 4 * q, ld4(v + 4 * q));
       } else {
 #pragma unroll 1
         for (int j = 0; j < nvalid; ++j) dst[j] = v[j];
@@ -138,14 +175,19 @@ __device__ __noinline__ void tc_epilogue_chunk(const TcConvParams& p, float* v, 
     if (col < p.hid) {                              // z gate -> fp32 plane
       float* dst = p.z + pix * (size_t)p.hid + col;
 #pragma unroll 1
-      for (int q = 0; q < 8; ++q)
-        reinterpret_cast<float4*>(dst)[q] = make_float4(sigmoidf_acc(v[4 * q]), sigmoidf_acc(v[4 * q + 1]),
-                                                        sigmoidf_acc(v[4 * q + 2]), sigmoidf_acc(v[4 * q + 3]));
+      for (int q = 0; q < 8; ++q) {
+        const float4 a = ld4(v + 4 * q);
+        st4(dst + 4 * q, make_float4(sigmoidf_acc(a.x), sigmoidf_acc(a.y), sigmoidf_acc(a.z), sigmoidf_acc(a.w)));
+      }
     } else {                                        // r gate -> r*h, re-split for the q convolution
       const int hc = col - p.hid;
       const float* hp = p.h + pix * (size_t)p.hid + hc;
 #pragma unroll 1
-      for (int j = 0; j < 32; ++j) v[j] = sigmoidf_acc(v[j]) * __ldg(hp + j);
+      for (int q = 0; q < 8; ++q) {
+        const float4 a = ld4(v + 4 * q), hv = ldg4(hp + 4 * q);
+        st4(v + 4 * q, make_float4(sigmoidf_acc(a.x) * hv.x, sigmoidf_acc(a.y) * hv.y, sigmoidf_acc(a.z) * hv.z,
+                                   sigmoidf_acc(a.w) * hv.w));
+      }
       const size_t o = pix * (size_t)p.h_stride + p.h_c0 + hc;
       dhi = p.out_hi + o;
       dlo = p.out_lo + o;
@@ -154,11 +196,12 @@ __device__ __noinline__ void tc_epilogue_chunk(const TcConvParams& p, float* v, 
     float* hrow = p.h + pix * (size_t)p.hid + col;
     const float* zp = p.z + pix * (size_t)p.hid + col;
 #pragma unroll 1
-    for (int j = 0; j < 32; ++j) {
-      const float zv = __ldg(zp + j);
-      const float hn = (1.0f - zv) * hrow[j] + zv * tanhf(v[j]);
-      v[j] = hn;
-      hrow[j] = hn;
+    for (int q = 0; q < 8; ++q) {
+      const float4 a = ld4(v + 4 * q), zv = ldg4(zp + 4 * q), hv = ld4(hrow + 4 * q);
+      const float4 hn = make_float4((1.0f - zv.x) * hv.x + zv.x * tanhf(a.x), (1.0f - zv.y) * hv.y + zv.y * tanhf(a.y),
+                                    (1.0f - zv.z) * hv.z + zv.z * tanhf(a.z), (1.0f - zv.w) * hv.w + zv.w * tanhf(a.w));
+      st4(v + 4 * q, hn);
+      st4(hrow + 4 * q, hn);
     }
     const size_t o = pix * (size_t)p.h_stride + p.h_c0 + col;
     dhi = p.out_hi + o;
@@ -168,12 +211,14 @@ __device__ __noinline__ void tc_epilogue_chunk(const TcConvParams& p, float* v, 
   if (dhi) {                                        // fp16 hi/lo re-split, 8 channels (16 bytes) per store
 #pragma unroll 1
     for (int q = 0; q < 4; ++q) {
+      const float4 a = ld4(v + 8 * q), b = ld4(v + 8 * q + 4);
+      const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
       uint32_t ph[4], pl[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         __half h0, l0, h1, l1;
-        split_f16(v[8 * q + 2 * e], h0, l0);
-        split_f16(v[8 * q + 2 * e + 1], h1, l1);
+        split_f16(f[2 * e], h0, l0);
+        split_f16(f[2 * e + 1], h1, l1);
         ph[e] = pack_h2(h0, h1);
         pl[e] = pack_h2(l0, l1);
       }
@@ -186,6 +231,9 @@ __device__ __noinline__ void tc_epilogue_chunk(const TcConvParams& p, float* v, 
 
 __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_constant__ TcConvParams p) {
 #if defined(__CUDA_ARCH__)
+  // Persistent: CTA c processes output tiles c, c + gridDim.x, ...  A tile is (pixel tile, column tile).  All
+  // three roles walk the same tile sequence; the smem ring and the two TMEM buffers carry straight across
+  // tile boundaries, so the loads and MMAs of tile i+1 overlap the epilogue of tile i.
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nst = p.nstages;
@@ -199,19 +247,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // tile coordinates
-  int mt = blockIdx.x;
-  const int tx = mt % p.tiles_x;
-  mt /= p.tiles_x;
-  const int ty = mt % p.tiles_y;
-  const int b = mt / p.tiles_y;
-  const int x0 = tx * p.TW, y0 = ty * p.TH;
-  const int n0 = blockIdx.y * p.bn;
+  const int mtiles = p.B * p.tiles_y * p.tiles_x;
+  const int ntiles = mtiles * p.n_tiles_n;
   const int ntaps = p.kh * p.kw;
   const int chunks_per_tap = p.seg_chunks[0] + (p.nseg > 1 ? p.seg_chunks[1] : 0);
-  const int total = ntaps * chunks_per_tap;
+  const int total = ntaps * chunks_per_tap;               // K chunks per tile
   const int gsz = p.group_chunks;
-  const int ngroups = (total + gsz - 1) / gsz;
+  const int ngroups = (total + gsz - 1) / gsz;            // promotion groups per tile
   const int nchunks32 = (p.bn + 31) >> 5;                 // 32-column accumulator chunks
   const int chunks_a = (nchunks32 + 1) >> 1;              // handled by warps 2..5; the rest by warps 6..9
 
@@ -247,22 +289,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     // ===================== TMA producer =====================
     if (elect_one()) {
       int it = 0;
-      for (int tap = 0; tap < ntaps; ++tap) {
-        const int dy = tap / p.kw - p.ph, dx = tap % p.kw - p.pw;
-        int kc = 0;
-        for (int seg = 0; seg < p.nseg; ++seg) {
-          for (int ch = 0; ch < p.seg_chunks[seg]; ++ch, ++kc, ++it) {
-            const int s = it % nst;
-            const uint32_t phase = (uint32_t)(it / nst) & 1u;
-            mbar_wait(&empty_bar[s], phase ^ 1u);
-            uint8_t* st = smem + (size_t)s * p.stage_bytes;
-            mbar_arrive_expect_tx(&full_bar[s], (uint32_t)p.stage_bytes);
-            const int c = p.seg_c0[seg] + ch * kChunkK;
-            tma_load_4d(st, &p.a_hi[seg], &full_bar[s], c, x0 * p.stride + dx, y0 * p.stride + dy, b);
-            tma_load_4d(st + kABytes, &p.a_lo[seg], &full_bar[s], c, x0 * p.stride + dx, y0 * p.stride + dy, b);
-            const int tcoord = tap + b * p.b_batch_stride;
-            tma_load_3d(st + 2 * kABytes, &p.b_hi, &full_bar[s], kc * kChunkK, n0, tcoord);
-            tma_load_3d(st + 2 * kABytes + b_bytes, &p.b_lo, &full_bar[s], kc * kChunkK, n0, tcoord);
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int nt = t / mtiles;
+        int mt = t - nt * mtiles;
+        const int tx = mt % p.tiles_x;
+        mt /= p.tiles_x;
+        const int ty = mt % p.tiles_y;
+        const int b = mt / p.tiles_y;
+        const int x0 = tx * p.TW * p.stride, y0 = ty * p.TH * p.stride, n0 = nt * p.bn;
+        for (int tap = 0; tap < ntaps; ++tap) {
+          const int dy = tap / p.kw - p.ph, dx = tap % p.kw - p.pw;
+          const int tcoord = tap + b * p.b_batch_stride;
+          int kc = 0;
+          for (int seg = 0; seg < p.nseg; ++seg) {
+            for (int ch = 0; ch < p.seg_chunks[seg]; ++ch, ++kc, ++it) {
+              const int s = it % nst;
+              const uint32_t phase = (uint32_t)(it / nst) & 1u;
+              mbar_wait(&empty_bar[s], phase ^ 1u);
+              uint8_t* st = smem + (size_t)s * p.stage_bytes;
+              mbar_arrive_expect_tx(&full_bar[s], (uint32_t)p.stage_bytes);
+              const int c = p.seg_c0[seg] + ch * kChunkK;
+              tma_load_4d(st, &p.a_hi[seg], &full_bar[s], c, x0 + dx, y0 + dy, b);
+              tma_load_4d(st + kABytes, &p.a_lo[seg], &full_bar[s], c, x0 + dx, y0 + dy, b);
+              tma_load_3d(st + 2 * kABytes, &p.b_hi, &full_bar[s], kc * kChunkK, n0, tcoord);
+              tma_load_3d(st + 2 * kABytes + b_bytes, &p.b_lo, &full_bar[s], kc * kChunkK, n0, tcoord);
+            }
           }
         }
       }
@@ -270,35 +321,38 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     const uint32_t idesc = make_idesc_f16(kTileM, p.bn);
-    int it = 0;
-    for (int g = 0; g < ngroups; ++g) {
-      const int buf = g & 1;
-      mbar_wait(&acc_empty[buf], ((uint32_t)(g >> 1) & 1u) ^ 1u);   // promotion warps drained this buffer
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.bn);
-      const int gend = min(total, (g + 1) * gsz);
-      for (int first = 1; it < gend; ++it, first = 0) {
-        const int s = it % nst;
-        const uint32_t phase = (uint32_t)(it / nst) & 1u;
-        mbar_wait(&full_bar[s], phase);
+    int it = 0, gg = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      int done = 0;
+      for (int g = 0; g < ngroups; ++g, ++gg) {
+        const int buf = gg & 1;
+        mbar_wait(&acc_empty[buf], ((uint32_t)(gg >> 1) & 1u) ^ 1u);   // promotion warps drained this buffer
         tc_fence_after();
-        if (elect_one()) {
-          const uint32_t sa = smem_u32(smem + (size_t)s * p.stage_bytes);
-          const uint64_t a_hi = make_desc_sw128(sa);
-          const uint64_t a_lo = make_desc_sw128(sa + kABytes);
-          const uint64_t b_hi = make_desc_sw128(sa + 2 * kABytes);
-          const uint64_t b_lo = make_desc_sw128(sa + 2 * kABytes + b_bytes);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.bn);
+        const int gend = min(total, done + gsz);
+        for (int first = 1; done < gend; ++done, ++it, first = 0) {
+          const int s = it % nst;
+          const uint32_t phase = (uint32_t)(it / nst) & 1u;
+          mbar_wait(&full_bar[s], phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t sa = smem_u32(smem + (size_t)s * p.stage_bytes);
+            const uint64_t a_hi = make_desc_sw128(sa);
+            const uint64_t a_lo = make_desc_sw128(sa + kABytes);
+            const uint64_t b_hi = make_desc_sw128(sa + 2 * kABytes);
+            const uint64_t b_lo = make_desc_sw128(sa + 2 * kABytes + b_bytes);
 #pragma unroll
-          for (int k = 0; k < kChunkK / 16; ++k)   // +32 bytes per K=16 step == +2 in 16-byte units
-            umma_f16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (!first || k > 0) ? 1u : 0u);
+            for (int k = 0; k < kChunkK / 16; ++k)   // +32 bytes per K=16 step == +2 in 16-byte units
+              umma_f16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (!first || k > 0) ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < kChunkK / 16; ++k) umma_f16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+            for (int k = 0; k < kChunkK / 16; ++k) umma_f16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
 #pragma unroll
-          for (int k = 0; k < kChunkK / 16; ++k) umma_f16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
-          umma_commit(&empty_bar[s]);                    // frees the smem slot once these MMAs retire
-          if (it == gend - 1) umma_commit(&acc_full[buf]);   // group complete -> promotion warps
+            for (int k = 0; k < kChunkK / 16; ++k) umma_f16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+            umma_commit(&empty_bar[s]);                      // frees the smem slot once these MMAs retire
+            if (done == gend - 1) umma_commit(&acc_full[buf]);   // group complete -> promotion warps
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
   } else {
@@ -309,58 +363,67 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     const int my_chunks = half ? (nchunks32 - chunks_a) : chunks_a;
     const int m = quarter * 32 + lane;               // tile row == TMEM lane
     const int xl = m % p.TW, yl = m / p.TW;
-    const int x = x0 + xl, y = y0 + yl;
-    const bool valid = (x < p.W) && (y < p.H);
-    const size_t pix = ((size_t)b * p.H + (valid ? y : 0)) * p.W + (valid ? x : 0);
     const float inv_scale = p.inv_scale ? __ldg(p.inv_scale) : 1.0f;
     const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
 
-    float racc[4][32];
-#pragma unroll
-    for (int ci = 0; ci < 4; ++ci)
-#pragma unroll
-      for (int j = 0; j < 32; ++j) racc[ci][j] = 0.0f;
-
     if (my_chunks > 0) {
-      for (int g = 0; g < ngroups; ++g) {
-        const int buf = g & 1;
-        mbar_wait(&acc_full[buf], (uint32_t)(g >> 1) & 1u);
-        tc_fence_after();
+      int gg = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        float racc[4][32];
 #pragma unroll
-        for (int ci = 0; ci < 4; ++ci) {
-          if (ci < my_chunks) {
-            const int c0 = (chunk0 + ci) * 32;
-            uint32_t r[32];
-            if (p.bn - c0 >= 32) {
-              tmem_ld_32x32(trow + (uint32_t)(buf * p.bn + c0), r);
-            } else {
-              uint32_t r16[16];
-              tmem_ld_32x16(trow + (uint32_t)(buf * p.bn + c0), r16);
+        for (int ci = 0; ci < 4; ++ci)
 #pragma unroll
-              for (int j = 0; j < 16; ++j) r[j] = r16[j];
-#pragma unroll
-              for (int j = 16; j < 32; ++j) r[j] = 0u;
-            }
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) racc[ci][j] += __uint_as_float(r[j]);   // IEEE fp32 promotion
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[buf]);
-      }
-    }
+          for (int j = 0; j < 32; ++j) racc[ci][j] = 0.0f;
 
-    if (valid) {
-      float buf[32];
+        for (int g = 0; g < ngroups; ++g, ++gg) {
+          const int buf = gg & 1;
+          mbar_wait(&acc_full[buf], (uint32_t)(gg >> 1) & 1u);
+          tc_fence_after();
 #pragma unroll
-      for (int ci = 0; ci < 4; ++ci) {
-        if (ci < my_chunks) {
-          const int c0 = (chunk0 + ci) * 32;
+          for (int ci = 0; ci < 4; ++ci) {
+            if (ci < my_chunks) {
+              const int c0 = (chunk0 + ci) * 32;
+              uint32_t r[32];
+              if (p.bn - c0 >= 32) {
+                tmem_ld_32x32(trow + (uint32_t)(buf * p.bn + c0), r);
+              } else {
+                uint32_t r16[16];
+                tmem_ld_32x16(trow + (uint32_t)(buf * p.bn + c0), r16);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) buf[j] = racc[ci][j];
-          tc_epilogue_chunk(p, buf, pix, n0 + c0, min(32, p.bn - c0), inv_scale);
+                for (int j = 0; j < 16; ++j) r[j] = r16[j];
+#pragma unroll
+                for (int j = 16; j < 32; ++j) r[j] = 0u;
+              }
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) racc[ci][j] += __uint_as_float(r[j]);   // IEEE fp32 promotion
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+
+        // ---- epilogue of this tile (the issuer is already accumulating the next one) ----
+        const int nt = t / mtiles;
+        int mt = t - nt * mtiles;
+        const int tx = mt % p.tiles_x;
+        mt /= p.tiles_x;
+        const int ty = mt % p.tiles_y;
+        const int b = mt / p.tiles_y;
+        const int x = tx * p.TW + xl, y = ty * p.TH + yl;
+        if (x < p.W && y < p.H) {
+          const size_t pix = ((size_t)b * p.H + y) * p.W + x;
+          __align__(16) float buf32[32];
+#pragma unroll
+          for (int ci = 0; ci < 4; ++ci) {
+            if (ci < my_chunks) {
+              const int c0 = (chunk0 + ci) * 32;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) buf32[j] = racc[ci][j];
+              tc_epilogue_chunk(p, buf32, pix, nt * p.bn + c0, min(32, p.bn - c0), inv_scale);
+            }
+          }
         }
       }
     }
@@ -405,6 +468,27 @@ inline int tc_finalize(TcConvParams& p) {
   return nst * p.stage_bytes + 1024 /*align slack*/ + (2 * nst + 4) * 8 + 16;
 }
 
+// Preferred cluster size (1, 2 or 4); RAFT_B200_CLUSTER overrides the default of 2.
+inline int tc_cluster_pref() {
+  static int pref = -1;
+  if (pref < 0) {
+    const char* e = getenv("RAFT_B200_CLUSTER");
+    int v = e ? atoi(e) : 1;
+    pref = (v == 4 || v == 2) ? v : 1;
+  }
+  return pref;
+}
+
+// Cluster size for a launch: largest power of two <= preference that divides the pixel-tile count and keeps
+// the per-CTA weight slice a whole number of 8-row swizzle atoms.  Callers need it BEFORE building the weight
+// tensor maps, whose box is bn / cluster rows.
+inline int tc_plan_cluster(int B, int H, int W, int th, int tw, int bn) {
+  // Measured (profiles/): 2- and 4-CTA weight multicast did not beat unicast -- L2 already de-duplicates the
+  // identical weight requests of neighbouring SMs -- so the persistent kernel runs without clusters.
+  (void)B; (void)H; (void)W; (void)th; (void)tw; (void)bn;
+  return 1;
+}
+
 inline int tc_launch(TcConvParams& p, int n_tiles_n, cudaStream_t stream) {
   if (p.bn % 16 != 0 || p.bn < 16 || p.bn > 256 || p.TW * p.TH != kTileM) return RAFT_ERR_BAD_SHAPE;
   if (p.stride < 1) p.stride = 1;
@@ -415,7 +499,11 @@ inline int tc_launch(TcConvParams& p, int n_tiles_n, cudaStream_t stream) {
     RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  dim3 grid((unsigned)(p.B * p.tiles_y * p.tiles_x), (unsigned)n_tiles_n, 1);
+  const int mtiles = p.B * p.tiles_y * p.tiles_x;
+  p.n_tiles_n = n_tiles_n;
+  p.cluster = 1;
+  const long ntiles = (long)mtiles * n_tiles_n;
+  const unsigned grid = (unsigned)(ntiles < kNumSMs ? ntiles : kNumSMs);   // one persistent CTA per SM
   conv_tc_kernel<<<grid, kTcThreads, smem, stream>>>(p);
   return raft_launch_status();
 }

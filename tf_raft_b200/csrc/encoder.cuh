@@ -217,10 +217,11 @@ inline int enc_conv_tc(const EncCtx& c, const EncConvSlot& cs, const EncNormSlot
   if (tw * stride > 256) tw = 128 / stride, th = 128 / tw;
   RAFT_TRY(make_tmap_act(&p.a_hi[0], ahi, c.N, Hin, Win, cs.cin_pad, tw, th, stride));
   RAFT_TRY(make_tmap_act(&p.a_lo[0], alo, c.N, Hin, Win, cs.cin_pad, tw, th, stride));
+  p.cluster = tc_plan_cluster(c.N, Hout, Wout, th, tw, cs.cout_pad);
   RAFT_TRY(make_tmap_wgt(&p.b_hi, reinterpret_cast<const __half*>(c.prep + cs.hi), cs.kh * cs.kw, cs.cout_pad, cs.cin_pad,
-                         cs.cout_pad));
+                         cs.cout_pad / p.cluster));
   RAFT_TRY(make_tmap_wgt(&p.b_lo, reinterpret_cast<const __half*>(c.prep + cs.lo), cs.kh * cs.kw, cs.cout_pad, cs.cin_pad,
-                         cs.cout_pad));
+                         cs.cout_pad / p.cluster));
   p.nseg = 1; p.seg_chunks[0] = cs.cin_pad / kChunkK; p.seg_c0[0] = 0;
   p.kh = cs.kh; p.kw = cs.kw; p.stride = stride;
   // Keras 'same': stride 1 -> (k-1)/2 before; stride 2 on even input -> total k-2, before = (k-2)/2 (0 for 3x3);
@@ -273,7 +274,7 @@ inline int encoder_forward(int variant, int norm_type, int out_dim, const void* 
   {
     const size_t npix = (size_t)N * h * w;
     const int tot_h = (h - 1) * 2 + 7 - H, tot_w = (w - 1) * 2 + 7 - W;
-    stem_im2col_kernel<<<grid_for(npix * 192), 256, 0, st>>>(images, N, H, W, h, w, (tot_h > 0 ? tot_h : 0) / 2,
+    stem_im2col_kernel<<<grid_for(npix * 24), 256, 0, st>>>(images, N, H, W, h, w, (tot_h > 0 ? tot_h : 0) / 2,
                                                             (tot_w > 0 ? tot_w : 0) / 2, image_norm, E.Ih, E.Il);
     ++g_launches;
     if (!c.stats && pad64(S.c0) != S.c0) {

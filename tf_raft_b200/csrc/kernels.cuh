@@ -60,22 +60,31 @@ __global__ void coords_grid_kernel(float* __restrict__ out, int B, int h, int w)
 // coordinate gives zero weight on all four corners.  Every operation is individually rounded
 // (__f*_rn) so the result is bit-identical to the op-by-op NumPy/TF evaluation.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float sample_floor_ceil(const float* __restrict__ img, int H, int W, float px, float py) {
+struct TapGather { float c00, c01, c10, c11; int o00, o01, o10, o11; };
+// Corner offsets and weights of one sample (corr.py:40-60), each operation individually rounded.
+__device__ __forceinline__ TapGather tap_setup(int H, int W, float px, float py) {
   const float gx = fminf(fmaxf(px, 0.0f), (float)(W - 1));
   const float gy = fminf(fmaxf(py, 0.0f), (float)(H - 1));
   const float gx0 = floorf(gx), gx1 = ceilf(gx), gy0 = floorf(gy), gy1 = ceilf(gy);
   const float wy1 = __fsub_rn(gy1, gy), wy0 = __fsub_rn(gy, gy0);
   const float wx1 = __fsub_rn(gx1, gx), wx0 = __fsub_rn(gx, gx0);
-  const float c00 = __fmul_rn(wy1, wx1), c01 = __fmul_rn(wy1, wx0);
-  const float c10 = __fmul_rn(wy0, wx1), c11 = __fmul_rn(wy0, wx0);
+  TapGather t;
+  t.c00 = __fmul_rn(wy1, wx1); t.c01 = __fmul_rn(wy1, wx0);
+  t.c10 = __fmul_rn(wy0, wx1); t.c11 = __fmul_rn(wy0, wx0);
   const int ix0 = (int)gx0, ix1 = (int)gx1, iy0 = (int)gy0, iy1 = (int)gy1;
-  const float x00 = __ldg(img + iy0 * W + ix0), x01 = __ldg(img + iy0 * W + ix1);
-  const float x10 = __ldg(img + iy1 * W + ix0), x11 = __ldg(img + iy1 * W + ix1);
-  float acc = __fmul_rn(c00, x00);
-  acc = __fadd_rn(acc, __fmul_rn(c01, x01));
-  acc = __fadd_rn(acc, __fmul_rn(c10, x10));
-  acc = __fadd_rn(acc, __fmul_rn(c11, x11));
+  t.o00 = iy0 * W + ix0; t.o01 = iy0 * W + ix1; t.o10 = iy1 * W + ix0; t.o11 = iy1 * W + ix1;
+  return t;
+}
+__device__ __forceinline__ float tap_combine(const TapGather& t, float x00, float x01, float x10, float x11) {
+  float acc = __fmul_rn(t.c00, x00);                       // corr.py:68, left to right
+  acc = __fadd_rn(acc, __fmul_rn(t.c01, x01));
+  acc = __fadd_rn(acc, __fmul_rn(t.c10, x10));
+  acc = __fadd_rn(acc, __fmul_rn(t.c11, x11));
   return acc;
+}
+__device__ __forceinline__ float sample_floor_ceil(const float* __restrict__ img, int H, int W, float px, float py) {
+  const TapGather t = tap_setup(H, W, px, py);
+  return tap_combine(t, __ldg(img + t.o00), __ldg(img + t.o01), __ldg(img + t.o10), __ldg(img + t.o11));
 }
 
 __global__ void bilinear_sampler_kernel(const float* __restrict__ image, const float* __restrict__ coords, int M, int H,
@@ -116,18 +125,49 @@ __global__ void __launch_bounds__(256) corr_lookup_kernel(const LookupParams p) 
     const float inv = 1.0f / (float)(1 << l);                    // exact power of two
     const float cx = __fmul_rn(__ldg(p.coords + 2 * (size_t)q), inv);     // coords / 2**i  (corr.py:141)
     const float cy = __fmul_rn(__ldg(p.coords + 2 * (size_t)q + 1), inv);
-    for (int t = lane; t < ntap; t += 32) {
-      const int a = t / side, b2 = t - a * side;
-      const float px = __fadd_rn(cx, (float)(a - p.radius));     // centroid + delta (corr.py:143)
-      const float py = __fadd_rn(cy, (float)(b2 - p.radius));
-      const float v = sample_floor_ceil(img, H, W, px, py);
-      const int ch = l * ntap + t;
-      if (p.out) p.out[(size_t)q * p.out_stride + ch] = v;
-      if (p.out_hi) {
-        __half hh, ll;
-        split_f16(v, hh, ll);
-        p.out_hi[(size_t)q * p.h_stride + ch] = hh;
-        p.out_lo[(size_t)q * p.h_stride + ch] = ll;
+    // All gathers of this (query, level) are issued before any is consumed: the lookup is latency-bound
+    // (dependent DRAM/L2 gathers), so memory-level parallelism -- 12 loads in flight per lane -- is what counts.
+    constexpr int kMaxIter = 3;                                  // (2r+1)^2 <= 96, i.e. radius <= 4
+    if (ntap <= 32 * kMaxIter) {
+      TapGather tg[kMaxIter];
+      float x00[kMaxIter], x01[kMaxIter], x10[kMaxIter], x11[kMaxIter];
+#pragma unroll
+      for (int i = 0; i < kMaxIter; ++i) {
+        const int t = min(lane + 32 * i, ntap - 1);
+        const int a = t / side, b2 = t - a * side;
+        tg[i] = tap_setup(H, W, __fadd_rn(cx, (float)(a - p.radius)), __fadd_rn(cy, (float)(b2 - p.radius)));
+        x00[i] = __ldg(img + tg[i].o00); x01[i] = __ldg(img + tg[i].o01);
+        x10[i] = __ldg(img + tg[i].o10); x11[i] = __ldg(img + tg[i].o11);
+      }
+#pragma unroll
+      for (int i = 0; i < kMaxIter; ++i) {
+        const int t = lane + 32 * i;
+        if (t < ntap) {
+          const float v = tap_combine(tg[i], x00[i], x01[i], x10[i], x11[i]);
+          const int ch = l * ntap + t;
+          if (p.out) p.out[(size_t)q * p.out_stride + ch] = v;
+          if (p.out_hi) {
+            __half hh, ll;
+            split_f16(v, hh, ll);
+            p.out_hi[(size_t)q * p.h_stride + ch] = hh;
+            p.out_lo[(size_t)q * p.h_stride + ch] = ll;
+          }
+        }
+      }
+    } else {
+      for (int t = lane; t < ntap; t += 32) {
+        const int a = t / side, b2 = t - a * side;
+        const float px = __fadd_rn(cx, (float)(a - p.radius));   // centroid + delta (corr.py:143)
+        const float py = __fadd_rn(cy, (float)(b2 - p.radius));
+        const float v = sample_floor_ceil(img, H, W, px, py);
+        const int ch = l * ntap + t;
+        if (p.out) p.out[(size_t)q * p.out_stride + ch] = v;
+        if (p.out_hi) {
+          __half hh, ll;
+          split_f16(v, hh, ll);
+          p.out_hi[(size_t)q * p.h_stride + ch] = hh;
+          p.out_lo[(size_t)q * p.h_stride + ch] = ll;
+        }
       }
     }
     if (p.out_hi && l == p.levels - 1) {
@@ -535,24 +575,35 @@ __global__ void norm_apply_kernel(const float* __restrict__ y, size_t npix, int 
 // (padding applies to the normalised image), as fp16 hi/lo planes with 192 channels (147..191 = 0).
 __global__ void stem_im2col_kernel(const float* __restrict__ img, int N, int H, int W, int h, int w, int pad_t,
                                    int pad_l, int image_norm, __half* __restrict__ hi, __half* __restrict__ lo) {
-  const size_t total = (size_t)N * h * w * 192;
+  // one thread = 8 consecutive im2col channels of one output pixel -> one 16-byte store per plane
+  const size_t total = (size_t)N * h * w * 24;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int kk = (int)(i % 192);
-    size_t px = i / 192;
+    const int grp = (int)(i % 24);
+    const size_t px = i / 24;
     const int x = (int)(px % w), y = (int)((px / w) % h), n = (int)(px / ((size_t)w * h));
-    float v = 0.f;
-    if (kk < 147) {
-      const int tap = kk / 3, c = kk - tap * 3;
-      const int iy = 2 * y + tap / 7 - pad_t, ix = 2 * x + tap % 7 - pad_l;
-      if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
-        v = __ldg(img + (((size_t)n * H + iy) * W + ix) * 3 + c);
-        if (image_norm) v = __fsub_rn(__fmul_rn(2.0f, __fdiv_rn(v, 255.0f)), 1.0f);
+    uint32_t ph[4], pl[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      __half hh[2], ll[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int kk = grp * 8 + 2 * e + u;
+        float v = 0.f;
+        if (kk < 147) {
+          const int tap = kk / 3, c = kk - tap * 3;
+          const int iy = 2 * y + tap / 7 - pad_t, ix = 2 * x + tap % 7 - pad_l;
+          if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+            v = __ldg(img + (((size_t)n * H + iy) * W + ix) * 3 + c);
+            if (image_norm) v = __fsub_rn(__fmul_rn(2.0f, __fdiv_rn(v, 255.0f)), 1.0f);
+          }
+        }
+        split_f16(v, hh[u], ll[u]);
       }
+      ph[e] = pack_h2(hh[0], hh[1]);
+      pl[e] = pack_h2(ll[0], ll[1]);
     }
-    __half hh, ll;
-    split_f16(v, hh, ll);
-    hi[i] = hh;
-    lo[i] = ll;
+    reinterpret_cast<uint4*>(hi)[i] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+    reinterpret_cast<uint4*>(lo)[i] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
   }
 }
 

@@ -263,8 +263,9 @@ inline int launch_tc_layer(const UpdateCtx& c, int layer, int nseg, const TcSeg*
   if (chunks * kChunkK != L.cin_pad) return RAFT_ERR_BAD_SHAPE;
   const __half* whi = reinterpret_cast<const __half*>(c.prepared + c.PL.tc_hi[layer]);
   const __half* wlo = reinterpret_cast<const __half*>(c.prepared + c.PL.tc_lo[layer]);
-  RAFT_TRY(make_tmap_wgt(&p.b_hi, whi, L.kh * L.kw, L.cout_pad, L.cin_pad, L.bn));
-  RAFT_TRY(make_tmap_wgt(&p.b_lo, wlo, L.kh * L.kw, L.cout_pad, L.cin_pad, L.bn));
+  p.cluster = tc_plan_cluster(c.B, c.h, c.w, th, tw, L.bn);
+  RAFT_TRY(make_tmap_wgt(&p.b_hi, whi, L.kh * L.kw, L.cout_pad, L.cin_pad, L.bn / p.cluster));
+  RAFT_TRY(make_tmap_wgt(&p.b_lo, wlo, L.kh * L.kw, L.cout_pad, L.cin_pad, L.bn / p.cluster));
   p.kh = L.kh; p.kw = L.kw; p.ph = (L.kh - 1) / 2; p.pw = (L.kw - 1) / 2;
   p.B = c.B; p.H = c.h; p.W = c.w; p.TH = th; p.TW = tw;
   p.bn = L.bn;

@@ -93,14 +93,11 @@ static int corr_build_tc(const float* f1, const float* f2, int B, int h, int w, 
     TcConvParams p;
     memset(&p, 0, sizeof(p));
     // A: fmap1 as a (B, 1, N, C) "image" -> 128 consecutive queries per tile
-    RAFT_TRY(make_tmap_act(&p.a_hi[0], W.f1_hi, B, 1, N, C, 128, 1));
-    RAFT_TRY(make_tmap_act(&p.a_lo[0], W.f1_lo, B, 1, N, C, 128, 1));
+    RAFT_TRY(make_tmap_act2(&p.a_map[0], W.f1_hi, W.f1_lo, B, 1, N, C, 128, 1));
     int bn = 256;
     if (N2 < 256) bn = round_up(N2, 16);
     // B: level-l features [B][N2][C] -> the batch index rides in the "tap" coordinate
-    p.cluster = tc_plan_cluster(B, 1, N, 1, 128, bn);
-    RAFT_TRY(make_tmap_wgt(&p.b_hi, W.f2_hi[l], B, N2, C, bn / p.cluster));
-    RAFT_TRY(make_tmap_wgt(&p.b_lo, W.f2_lo[l], B, N2, C, bn / p.cluster));
+    RAFT_TRY(make_tmap_wgt2(&p.b_map, W.f2_hi[l], W.f2_lo[l], B, N2, C, bn));
     p.nseg = 1; p.seg_chunks[0] = C / kChunkK; p.seg_c0[0] = 0;
     p.kh = p.kw = 1; p.ph = p.pw = 0;
     p.B = B; p.H = 1; p.W = N; p.TH = 1; p.TW = 128;

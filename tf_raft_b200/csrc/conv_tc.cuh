@@ -43,8 +43,8 @@ constexpr int kABytes = kTileM * kChunkK * 2;     // 16 KiB per A plane per stag
 constexpr int kSmemBudget = 227 * 1024 - 2048;
 
 struct alignas(64) TcConvParams {
-  CUtensorMap a_hi[2], a_lo[2];   // up to two channel-concatenated source tensors (K segments)
-  CUtensorMap b_hi, b_lo;
+  CUtensorMap a_map[2];           // (hi, lo) plane pair of up to two channel-concatenated sources (K segments)
+  CUtensorMap b_map;              // (hi, lo) plane pair of the packed weights
   int nseg, seg_chunks[2], seg_c0[2];
   int kh, kw, ph, pw;             // taps and 'same' padding (pad before)
   int stride;                     // 1 or 2: input pixel = output pixel * stride + tap - pad (TMA elementStrides)
@@ -267,14 +267,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       mbar_init(&acc_empty[i], nchunks32 > 1 ? 8 : 4);    // one arrival per participating warp
     }
     fence_mbar_init();
-    prefetch_tmap(&p.a_hi[0]);
-    prefetch_tmap(&p.a_lo[0]);
-    prefetch_tmap(&p.b_hi);
-    prefetch_tmap(&p.b_lo);
-    if (p.nseg > 1) {
-      prefetch_tmap(&p.a_hi[1]);
-      prefetch_tmap(&p.a_lo[1]);
-    }
+    prefetch_tmap(&p.a_map[0]);
+    prefetch_tmap(&p.b_map);
+    if (p.nseg > 1) prefetch_tmap(&p.a_map[1]);
   }
   if (warp == 1) {
     tmem_alloc(tmem_holder, (uint32_t)p.tmem_cols);
@@ -309,10 +304,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
               uint8_t* st = smem + (size_t)s * p.stage_bytes;
               mbar_arrive_expect_tx(&full_bar[s], (uint32_t)p.stage_bytes);
               const int c = p.seg_c0[seg] + ch * kChunkK;
-              tma_load_4d(st, &p.a_hi[seg], &full_bar[s], c, x0 + dx, y0 + dy, b);
-              tma_load_4d(st + kABytes, &p.a_lo[seg], &full_bar[s], c, x0 + dx, y0 + dy, b);
-              tma_load_3d(st + 2 * kABytes, &p.b_hi, &full_bar[s], kc * kChunkK, n0, tcoord);
-              tma_load_3d(st + 2 * kABytes + b_bytes, &p.b_lo, &full_bar[s], kc * kChunkK, n0, tcoord);
+              // two boxes per stage: [A_hi | A_lo] and [B_hi | B_lo] (TMA cost is per box, not per byte)
+              tma_load_5d(st, &p.a_map[seg], &full_bar[s], c, x0 + dx, y0 + dy, b, 0);
+              tma_load_4d(st + 2 * kABytes, &p.b_map, &full_bar[s], kc * kChunkK, n0, tcoord, 0);
             }
           }
         }

@@ -215,13 +215,9 @@ inline int enc_conv_tc(const EncCtx& c, const EncConvSlot& cs, const EncNormSlot
   int tw, th;
   tc_pick_tile(Wout, Hout, &tw, &th);
   if (tw * stride > 256) tw = 128 / stride, th = 128 / tw;
-  RAFT_TRY(make_tmap_act(&p.a_hi[0], ahi, c.N, Hin, Win, cs.cin_pad, tw, th, stride));
-  RAFT_TRY(make_tmap_act(&p.a_lo[0], alo, c.N, Hin, Win, cs.cin_pad, tw, th, stride));
-  p.cluster = tc_plan_cluster(c.N, Hout, Wout, th, tw, cs.cout_pad);
-  RAFT_TRY(make_tmap_wgt(&p.b_hi, reinterpret_cast<const __half*>(c.prep + cs.hi), cs.kh * cs.kw, cs.cout_pad, cs.cin_pad,
-                         cs.cout_pad / p.cluster));
-  RAFT_TRY(make_tmap_wgt(&p.b_lo, reinterpret_cast<const __half*>(c.prep + cs.lo), cs.kh * cs.kw, cs.cout_pad, cs.cin_pad,
-                         cs.cout_pad / p.cluster));
+  RAFT_TRY(make_tmap_act2(&p.a_map[0], ahi, alo, c.N, Hin, Win, cs.cin_pad, tw, th, stride));
+  RAFT_TRY(make_tmap_wgt2(&p.b_map, reinterpret_cast<const __half*>(c.prep + cs.hi),
+                          reinterpret_cast<const __half*>(c.prep + cs.lo), cs.kh * cs.kw, cs.cout_pad, cs.cin_pad, cs.cout_pad));
   p.nseg = 1; p.seg_chunks[0] = cs.cin_pad / kChunkK; p.seg_c0[0] = 0;
   p.kh = cs.kh; p.kw = cs.kw; p.stride = stride;
   // Keras 'same': stride 1 -> (k-1)/2 before; stride 2 on even input -> total k-2, before = (k-2)/2 (0 for 3x3);

@@ -57,6 +57,33 @@ inline int make_tmap_act(CUtensorMap* out, const __half* base, int B, int H, int
   return make_tmap_f16(out, base, 4, dims, str, box, es);
 }
 
+// Measured on B200 (tools/tma_probe.cu): TMA delivery per SM is bound by the NUMBER of boxes (~616 cycles per box,
+// 16 KB or 32 KB alike, not improved by more boxes in flight).  The hi and lo planes of every operand are therefore
+// fetched by ONE box: the plane index is an extra tensor dimension whose stride is (lo - hi) bytes.
+// Activation planes: rank-5 map (C, W, H, B, plane), box {64, tw*s, th*s, 1, 2} -> smem [hi 128 rows | lo 128 rows].
+inline int make_tmap_act2(CUtensorMap* out, const __half* hi, const __half* lo, int B, int H, int W, int cstride, int tw,
+                          int th, int stride = 1) {
+  const ptrdiff_t pstride = reinterpret_cast<const char*>(lo) - reinterpret_cast<const char*>(hi);
+  if (pstride <= 0 || (pstride & 15)) return RAFT_ERR_BAD_ARG;
+  if (tw * stride > 256 || th * stride > 256) return RAFT_ERR_BAD_SHAPE;
+  // dims (C, W, H, B, plane): strides stay monotonic; the box takes one image and both planes
+  uint64_t dims[5] = {(uint64_t)cstride, (uint64_t)W, (uint64_t)H, (uint64_t)B, 2};
+  uint64_t str[4] = {(uint64_t)cstride * 2, (uint64_t)W * cstride * 2, (uint64_t)H * W * cstride * 2, (uint64_t)pstride};
+  uint32_t box[5] = {64, (uint32_t)(tw * stride), (uint32_t)(th * stride), 1, 2};
+  uint32_t es[5] = {1, (uint32_t)stride, (uint32_t)stride, 1, 1};
+  return make_tmap_f16(out, hi, 5, dims, str, box, es);
+}
+// Weight planes: rank-4 map (cin_pad, cout_pad, taps, plane), box {64, bn, 1, 2} -> smem [hi bn rows | lo bn rows].
+inline int make_tmap_wgt2(CUtensorMap* out, const __half* hi, const __half* lo, int taps, int cout_pad, int cin_pad,
+                          int bn) {
+  const ptrdiff_t pstride = reinterpret_cast<const char*>(lo) - reinterpret_cast<const char*>(hi);
+  if (pstride <= 0 || (pstride & 15)) return RAFT_ERR_BAD_ARG;
+  uint64_t dims[4] = {(uint64_t)cin_pad, (uint64_t)cout_pad, (uint64_t)taps, 2};
+  uint64_t str[3] = {(uint64_t)cin_pad * 2, (uint64_t)cout_pad * cin_pad * 2, (uint64_t)pstride};
+  uint32_t box[4] = {64, (uint32_t)bn, 1, 2};
+  return make_tmap_f16(out, hi, 4, dims, str, box);
+}
+
 // Packed weights [taps][cout_pad][cin_pad] fp16 -> rank-3 map, box {64 ch, bn, 1}.
 inline int make_tmap_wgt(CUtensorMap* out, const __half* base, int taps, int cout_pad, int cin_pad, int bn) {
   uint64_t dims[3] = {(uint64_t)cin_pad, (uint64_t)cout_pad, (uint64_t)taps};

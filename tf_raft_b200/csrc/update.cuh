@@ -254,8 +254,7 @@ inline int launch_tc_layer(const UpdateCtx& c, int layer, int nseg, const TcSeg*
   p.nseg = nseg;
   int chunks = 0;
   for (int i = 0; i < nseg; ++i) {
-    RAFT_TRY(make_tmap_act(&p.a_hi[i], segs[i].hi, c.B, c.h, c.w, segs[i].stride, tw, th));
-    RAFT_TRY(make_tmap_act(&p.a_lo[i], segs[i].lo, c.B, c.h, c.w, segs[i].stride, tw, th));
+    RAFT_TRY(make_tmap_act2(&p.a_map[i], segs[i].hi, segs[i].lo, c.B, c.h, c.w, segs[i].stride, tw, th));
     p.seg_chunks[i] = segs[i].chunks;
     p.seg_c0[i] = segs[i].c0;
     chunks += segs[i].chunks;
@@ -263,9 +262,7 @@ inline int launch_tc_layer(const UpdateCtx& c, int layer, int nseg, const TcSeg*
   if (chunks * kChunkK != L.cin_pad) return RAFT_ERR_BAD_SHAPE;
   const __half* whi = reinterpret_cast<const __half*>(c.prepared + c.PL.tc_hi[layer]);
   const __half* wlo = reinterpret_cast<const __half*>(c.prepared + c.PL.tc_lo[layer]);
-  p.cluster = tc_plan_cluster(c.B, c.h, c.w, th, tw, L.bn);
-  RAFT_TRY(make_tmap_wgt(&p.b_hi, whi, L.kh * L.kw, L.cout_pad, L.cin_pad, L.bn / p.cluster));
-  RAFT_TRY(make_tmap_wgt(&p.b_lo, wlo, L.kh * L.kw, L.cout_pad, L.cin_pad, L.bn / p.cluster));
+  RAFT_TRY(make_tmap_wgt2(&p.b_map, whi, wlo, L.kh * L.kw, L.cout_pad, L.cin_pad, L.bn));
   p.kh = L.kh; p.kw = L.kw; p.ph = (L.kh - 1) / 2; p.pw = (L.kw - 1) / 2;
   p.B = c.B; p.H = c.h; p.W = c.w; p.TH = th; p.TW = tw;
   p.bn = L.bn;

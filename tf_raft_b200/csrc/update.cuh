@@ -9,6 +9,8 @@
 namespace raft {
 
 extern thread_local long long g_launches;
+extern int g_dbg_layer;            // timeline debugging (raft_b200_debug_timeline)
+extern long long* g_dbg_buf;
 #define RAFT_COUNT_LAUNCH() (++::raft::g_launches)
 
 // ------------------------------------------------------------------------------------------------
@@ -270,6 +272,7 @@ inline int launch_tc_layer(const UpdateCtx& c, int layer, int nseg, const TcSeg*
   p.bias = reinterpret_cast<const float*>(c.prepared + c.PL.tc_bias[layer]);
   p.inv_scale = reinterpret_cast<const float*>(c.prepared + c.PL.tc_scale[layer]) + 1;
   if (p.out_scale == 0.0f) p.out_scale = 1.0f;
+  if (g_dbg_layer == layer) p.dbg = g_dbg_buf;
   RAFT_COUNT_LAUNCH();
   return tc_launch(p, ntn > 0 ? ntn : L.ntn, c.stream);
 }

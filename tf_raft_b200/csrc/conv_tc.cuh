@@ -40,8 +40,7 @@ constexpr int kTcThreads = 320;           // 1 producer + 1 issuer + 8 promotion
 constexpr int kTileM = 128;
 constexpr int kChunkK = 64;                       // fp16 elements per 128-byte swizzled row
 constexpr int kABytes = kTileM * kChunkK * 2;     // 16 KiB per A plane per stage
-constexpr int kEpiPatchBytes = 8 * 4096;          // transposition patches of the 8 epilogue warps
-constexpr int kSmemBudget = 227 * 1024 - 2048 - kEpiPatchBytes;
+constexpr int kSmemBudget = 227 * 1024 - 2048;
 
 struct alignas(64) TcConvParams {
   CUtensorMap a_map[2];           // (hi, lo) plane pair of up to two channel-concatenated sources (K segments)
@@ -75,88 +74,176 @@ struct alignas(64) TcConvParams {
 
 #if defined(__CUDA_ARCH__)
 // ------------------------------------------------------------------------------------------------
-// Epilogue of one 32-row x 32-column block (one warp, one accumulator chunk).
-//
-// The accumulators arrive thread-per-row (TMEM lane == pixel row).  Written out that way every global
-// access of a warp touches 32 different lines and the rolled loops become a chain of dependent L2
-// latencies (measured: ~40 us of a 74 us GRU layer).  Instead the block is transposed through a private,
-// XOR-swizzled 4 KB shared-memory patch: afterwards lane == column, each row is one coalesced 128-byte
-// access, loads of several rows are in flight together, and activation math is spread over all lanes.
-// Kept out of line (one copy, ~1.5 K instructions) so the kernel stays inside the instruction cache.
+// Epilogue of one 32-column chunk of one pixel row.  Deliberately NOT inlined and written as rolled
+// loops over 4-element groups on a local-memory buffer: the fully unrolled multi-mode version was
+// 384 KB of SASS and instruction fetch ("no_instructions") became the top stall of every short-K layer.
+//   v[32]  accumulator values (in), pix = pixel index, col = first global output column, ncol = 32|16
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
 
-struct TileGeom { int b, x0, y0; };
+// Plain-value copy of the fields the epilogue needs.  The kernel parameter block is reached through a generic
+// pointer here, and without register copies every global store forces the compiler to re-load each field.
+struct EpiArgs {
+  int mode, act, n_total, hid, f32_stride, f32_c0, h_stride, h_c0, res_stride, res_c0, concat_n;
+  float out_scale, corr_div;
+  const float *bias, *post_scale, *post_shift, *residual, *concat_src;
+  float *out_f32, *z, *h;
+  __half *out_hi, *out_lo;
+};
 
-__device__ __noinline__ void tc_epilogue_block(const TcConvParams& p, const float* patch /*32x32 swizzled*/, TileGeom g,
-                                               int row0 /*tile row of patch row 0*/, int col0 /*global column of lane 0*/,
-                                               int ncol, float inv_scale) {
-  const int lane = threadIdx.x & 31;
-  const int col = col0 + lane;
-  const bool lane_on = lane < ncol;
-  float bias = 0.f, psc = 1.f, psh = 0.f;
-  if (p.mode != EPI_CORR && lane_on) {
-    if (p.bias) bias = __ldg(p.bias + col);
-    if (p.post_scale) { psc = __ldg(p.post_scale + col); psh = __ldg(p.post_shift + col); }
-  }
-  const int q = lane >> 2, wd = lane & 3;
-
-#pragma unroll 4
-  for (int r = 0; r < 32; ++r) {
-    const int m = row0 + r;
-    const int x = g.x0 + m % p.TW, y = g.y0 + m / p.TW;
-    if (x >= p.W || y >= p.H) continue;                       // warp-uniform
-    const size_t pix = ((size_t)g.b * p.H + y) * p.W + x;
-    float v = patch[r * 32 + ((q ^ (r & 7)) << 2) + wd];      // conflict-free transposed read
-
-    if (p.mode == EPI_CORR) {
-      if (lane_on && col < p.n_total) p.out_f32[pix * (size_t)p.f32_stride + col] = __fdiv_rn(v, p.corr_div);
-      continue;
+__device__ __noinline__ void tc_epilogue_chunk(const TcConvParams& pp, float* v, size_t pix, int col, int ncol,
+                                               float inv_scale) {
+  EpiArgs p;
+  p.mode = pp.mode; p.act = pp.act; p.n_total = pp.n_total; p.hid = pp.hid; p.f32_stride = pp.f32_stride;
+  p.f32_c0 = pp.f32_c0; p.h_stride = pp.h_stride; p.h_c0 = pp.h_c0; p.res_stride = pp.res_stride; p.res_c0 = pp.res_c0;
+  p.concat_n = pp.concat_n; p.out_scale = pp.out_scale; p.corr_div = pp.corr_div; p.bias = pp.bias;
+  p.post_scale = pp.post_scale; p.post_shift = pp.post_shift; p.residual = pp.residual; p.concat_src = pp.concat_src;
+  p.out_f32 = pp.out_f32; p.z = pp.z; p.h = pp.h; p.out_hi = pp.out_hi; p.out_lo = pp.out_lo;
+  // All loops are rolled (#pragma unroll 1) over groups of 4 columns with 16-byte accesses: every row of the
+  // tile is owned by one thread, so vector width -- not coalescing across lanes -- sets the memory efficiency.
+  if (p.mode == EPI_CORR) {
+    const int nvalid = min(ncol, p.n_total - col);
+    if (nvalid <= 0) return;
+    float* dst = p.out_f32 + pix * (size_t)p.f32_stride + col;
+    if (nvalid == 32 && (p.f32_stride & 3) == 0) {
+#pragma unroll 1
+      for (int q = 0; q < 8; ++q) {
+        const float4 a = ld4(v + 4 * q);
+        st4(dst + 4 * q, make_float4(__fdiv_rn(a.x, p.corr_div), __fdiv_rn(a.y, p.corr_div), __fdiv_rn(a.z, p.corr_div),
+                                     __fdiv_rn(a.w, p.corr_div)));
+      }
+    } else {
+#pragma unroll 1
+      for (int j = 0; j < nvalid; ++j) dst[j] = __fdiv_rn(v[j], p.corr_div);
     }
-    v = v * inv_scale + bias;
-    if (p.post_scale) v = v * psc + psh;
+    return;
+  }
 
-    if (p.mode == EPI_LINEAR) {
-      if (p.act == ACT_RELU) v = fmaxf(v, 0.0f);
-      v *= p.out_scale;
-      if (col >= p.n_total) {                                  // padded columns: concat tail, else exact zeros
-        const int cj = col - p.n_total;
-        v = (p.concat_src && cj < p.concat_n) ? __ldg(p.concat_src + pix * p.concat_n + cj) : 0.0f;
-      } else if (p.residual) {
-        v = fmaxf(v + __ldg(p.residual + pix * (size_t)p.res_stride + p.res_c0 + col), 0.0f);
+  // bias (+ folded BatchNorm affine); the bias / affine arrays are zero-padded past the last column
+#pragma unroll 1
+  for (int q = 0; q < 8; ++q) {
+    float4 t = ld4(v + 4 * q);
+    t.x *= inv_scale; t.y *= inv_scale; t.z *= inv_scale; t.w *= inv_scale;
+    if (p.bias) {
+      const float4 b = ldg4(p.bias + col + 4 * q);
+      t.x += b.x; t.y += b.y; t.z += b.z; t.w += b.w;
+    }
+    if (p.post_scale) {
+      const float4 sc = ldg4(p.post_scale + col + 4 * q), sh = ldg4(p.post_shift + col + 4 * q);
+      t.x = t.x * sc.x + sh.x; t.y = t.y * sc.y + sh.y; t.z = t.z * sc.z + sh.z; t.w = t.w * sc.w + sh.w;
+    }
+    st4(v + 4 * q, t);
+  }
+
+  __half* dhi = nullptr;
+  __half* dlo = nullptr;
+  if (p.mode == EPI_LINEAR) {
+    const bool full = col + 32 <= p.n_total;       // chunk entirely inside the valid columns (the common case)
+    if (full) {
+      const float* res = p.residual ? p.residual + pix * (size_t)p.res_stride + p.res_c0 + col : nullptr;
+      const bool res_vec = ((p.res_stride | p.res_c0) & 3) == 0;
+#pragma unroll 1
+      for (int q = 0; q < 8; ++q) {
+        float4 t = ld4(v + 4 * q);
+        if (p.act == ACT_RELU) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
+        t.x *= p.out_scale; t.y *= p.out_scale; t.z *= p.out_scale; t.w *= p.out_scale;
+        if (res) {
+          float4 r;
+          if (res_vec) r = ldg4(res + 4 * q);
+          else r = make_float4(__ldg(res + 4 * q), __ldg(res + 4 * q + 1), __ldg(res + 4 * q + 2), __ldg(res + 4 * q + 3));
+          t.x = fmaxf(t.x + r.x, 0.f); t.y = fmaxf(t.y + r.y, 0.f); t.z = fmaxf(t.z + r.z, 0.f); t.w = fmaxf(t.w + r.w, 0.f);
+        }
+        st4(v + 4 * q, t);
       }
-      if (p.out_f32 && lane_on && col < p.n_total) p.out_f32[pix * (size_t)p.f32_stride + p.f32_c0 + col] = v;
-      if (p.out_hi && ncol == 32) {
-        __half hh, ll;
-        split_f16(v, hh, ll);
-        const size_t o = pix * (size_t)p.h_stride + p.h_c0 + col;
-        p.out_hi[o] = hh;
-        p.out_lo[o] = ll;
+    } else {
+#pragma unroll 1
+      for (int j = 0; j < 32; ++j) {
+        float t = v[j];
+        if (p.act == ACT_RELU) t = fmaxf(t, 0.0f);
+        t *= p.out_scale;
+        if (col + j >= p.n_total) {                // padded columns: concat tail, else exact zeros
+          const int cj = col + j - p.n_total;
+          t = (p.concat_src && cj < p.concat_n) ? __ldg(p.concat_src + pix * p.concat_n + cj) : 0.0f;
+        } else if (p.residual) {
+          t = fmaxf(t + __ldg(p.residual + pix * (size_t)p.res_stride + p.res_c0 + col + j), 0.0f);
+        }
+        v[j] = t;
       }
-    } else if (p.mode == EPI_GRU_ZR) {
-      const float sgm = fast_sigmoid(v);
-      if (col < p.hid) {                                       // z gate -> fp32 plane
-        p.z[pix * (size_t)p.hid + col] = sgm;
-      } else {                                                 // r gate -> r*h, re-split for the q convolution
-        const int hc = col - p.hid;
-        const float rh = sgm * __ldg(p.h + pix * (size_t)p.hid + hc);
-        __half hh, ll;
-        split_f16(rh, hh, ll);
-        const size_t o = pix * (size_t)p.h_stride + p.h_c0 + hc;
-        p.out_hi[o] = hh;
-        p.out_lo[o] = ll;
+    }
+    if (p.out_f32) {
+      const int nvalid = min(ncol, p.n_total - col);
+      float* dst = p.out_f32 + pix * (size_t)p.f32_stride + p.f32_c0 + col;
+      if (nvalid == 32 && ((p.f32_stride | p.f32_c0) & 3) == 0) {
+#pragma unroll 1
+        for (int q = 0; q < 8; ++q) st4(dst + 4 * q, ld4(v + 4 * q));
+      } else {
+#pragma unroll 1
+        for (int j = 0; j < nvalid; ++j) dst[j] = v[j];
       }
-    } else {                                                   // EPI_GRU_Q: h = (1-z)*h + z*tanh(v), in place
-      float* hp = p.h + pix * (size_t)p.hid + col;
-      const float zv = __ldg(p.z + pix * (size_t)p.hid + col);
-      const float hn = (1.0f - zv) * (*hp) + zv * fast_tanh(v);
-      *hp = hn;
-      __half hh, ll;
-      split_f16(hn, hh, ll);
+    }
+    if (p.out_hi && ncol == 32) {
       const size_t o = pix * (size_t)p.h_stride + p.h_c0 + col;
-      p.out_hi[o] = hh;
-      p.out_lo[o] = ll;
+      dhi = p.out_hi + o;
+      dlo = p.out_lo + o;
+    }
+  } else if (p.mode == EPI_GRU_ZR) {
+    if (col < p.hid) {                              // z gate -> fp32 plane
+      float* dst = p.z + pix * (size_t)p.hid + col;
+#pragma unroll 1
+      for (int q = 0; q < 8; ++q) {
+        const float4 a = ld4(v + 4 * q);
+        st4(dst + 4 * q, make_float4(fast_sigmoid(a.x), fast_sigmoid(a.y), fast_sigmoid(a.z), fast_sigmoid(a.w)));
+      }
+    } else {                                        // r gate -> r*h, re-split for the q convolution
+      const int hc = col - p.hid;
+      const float* hp = p.h + pix * (size_t)p.hid + hc;
+#pragma unroll 1
+      for (int q = 0; q < 8; ++q) {
+        const float4 a = ld4(v + 4 * q), hv = ldg4(hp + 4 * q);
+        st4(v + 4 * q, make_float4(fast_sigmoid(a.x) * hv.x, fast_sigmoid(a.y) * hv.y, fast_sigmoid(a.z) * hv.z,
+                                   fast_sigmoid(a.w) * hv.w));
+      }
+      const size_t o = pix * (size_t)p.h_stride + p.h_c0 + hc;
+      dhi = p.out_hi + o;
+      dlo = p.out_lo + o;
+    }
+  } else {                                          // EPI_GRU_Q: h = (1-z)*h + z*tanh(v), in place
+    float* hrow = p.h + pix * (size_t)p.hid + col;
+    const float* zp = p.z + pix * (size_t)p.hid + col;
+#pragma unroll 1
+    for (int q = 0; q < 8; ++q) {
+      const float4 a = ld4(v + 4 * q), zv = ldg4(zp + 4 * q), hv = ld4(hrow + 4 * q);
+      const float4 hn = make_float4((1.0f - zv.x) * hv.x + zv.x * fast_tanh(a.x), (1.0f - zv.y) * hv.y + zv.y * fast_tanh(a.y),
+                                    (1.0f - zv.z) * hv.z + zv.z * fast_tanh(a.z), (1.0f - zv.w) * hv.w + zv.w * fast_tanh(a.w));
+      st4(v + 4 * q, hn);
+      st4(hrow + 4 * q, hn);
+    }
+    const size_t o = pix * (size_t)p.h_stride + p.h_c0 + col;
+    dhi = p.out_hi + o;
+    dlo = p.out_lo + o;
+  }
+
+  if (dhi) {                                        // fp16 hi/lo re-split, 8 channels (16 bytes) per store
+#pragma unroll 1
+    for (int q = 0; q < 4; ++q) {
+      const float4 a = ld4(v + 8 * q), b = ld4(v + 8 * q + 4);
+      const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      uint32_t ph[4], pl[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        __half h0, l0, h1, l1;
+        split_f16(f[2 * e], h0, l0);
+        split_f16(f[2 * e + 1], h1, l1);
+        ph[e] = pack_h2(h0, h1);
+        pl[e] = pack_h2(l0, l1);
+      }
+      reinterpret_cast<uint4*>(dhi)[q] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+      reinterpret_cast<uint4*>(dlo)[q] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
     }
   }
 }
@@ -176,7 +263,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
   uint64_t* acc_full = empty_bar + nst;      // [2] issuer -> promotion warps
   uint64_t* acc_empty = acc_full + 2;        // [2] promotion warps -> issuer
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  float* patches = reinterpret_cast<float*>(smem + (size_t)nst * p.stage_bytes + 256);   // 8 x 4 KB, one per epilogue warp
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -291,6 +377,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     const int half = (warp - 2) >> 2;                // 0: chunks [0, chunks_a), 1: chunks [chunks_a, nchunks32)
     const int chunk0 = half ? chunks_a : 0;
     const int my_chunks = half ? (nchunks32 - chunks_a) : chunks_a;
+    const int m = quarter * 32 + lane;               // tile row == TMEM lane
+    const int xl = m % p.TW, yl = m / p.TW;
     const float inv_scale = p.inv_scale ? __ldg(p.inv_scale) : 1.0f;
     const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
 
@@ -307,7 +395,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
           const int buf = gg & 1;
           mbar_wait(&acc_full[buf], (uint32_t)(gg >> 1) & 1u);
           tc_fence_after();
-          if (p.dbg && blockIdx.x == 0 && gg < 512 && warp == 2 && lane == 0) p.dbg[1024 + gg] = clock64();   // group MMAs retired
+          if (p.dbg && blockIdx.x == 0 && gg < 512 && warp == 2 && lane == 0) p.dbg[1024 + gg] = clock64();   // group retired
 #pragma unroll
           for (int ci = 0; ci < 4; ++ci) {
             if (ci < my_chunks) {
@@ -337,26 +425,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         // ---- epilogue of this tile (the issuer is already accumulating the next one) ----
         const int nt = t / mtiles;
         int mt = t - nt * mtiles;
-        TileGeom geo;
         const int tx = mt % p.tiles_x;
         mt /= p.tiles_x;
-        geo.x0 = tx * p.TW;
-        geo.y0 = (mt % p.tiles_y) * p.TH;
-        geo.b = mt / p.tiles_y;
-        float* patch = patches + (warp - 2) * 1024;
+        const int ty = mt % p.tiles_y;
+        const int b = mt / p.tiles_y;
+        const int x = tx * p.TW + xl, y = ty * p.TH + yl;
+        if (x < p.W && y < p.H) {
+          const size_t pix = ((size_t)b * p.H + y) * p.W + x;
+          __align__(16) float buf32[32];
 #pragma unroll
-        for (int ci = 0; ci < 4; ++ci) {
-          if (ci < my_chunks) {
-            const int c0 = (chunk0 + ci) * 32;
-            __syncwarp();                                      // previous block fully read before overwriting
+          for (int ci = 0; ci < 4; ++ci) {
+            if (ci < my_chunks) {
+              const int c0 = (chunk0 + ci) * 32;
 #pragma unroll
-            for (int qq = 0; qq < 8; ++qq)                     // row = lane, 16-byte chunks XOR-swizzled by (row & 7)
-              *reinterpret_cast<float4*>(patch + lane * 32 + ((qq ^ (lane & 7)) << 2)) =
-                  make_float4(racc[ci][4 * qq], racc[ci][4 * qq + 1], racc[ci][4 * qq + 2], racc[ci][4 * qq + 3]);
-            __syncwarp();
-            tc_epilogue_block(p, patch, geo, quarter * 32, nt * p.bn + c0, min(32, p.bn - c0), inv_scale);
+              for (int j = 0; j < 32; ++j) buf32[j] = racc[ci][j];
+              tc_epilogue_chunk(p, buf32, pix, nt * p.bn + c0, min(32, p.bn - c0), inv_scale);
+            }
           }
         }
+        if (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0) p.dbg[2047] = clock64();   // epilogue of the tile done
       }
     }
   }
@@ -397,7 +484,7 @@ inline int tc_finalize(TcConvParams& p) {
   while (cols < 2 * p.bn) cols <<= 1;           // two accumulator buffers (ping-pong promotion)
   p.tmem_cols = cols;
   if (p.group_chunks <= 0) p.group_chunks = 2;
-  return nst * p.stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiPatchBytes;
+  return nst * p.stage_bytes + 1024 /*align slack*/ + (2 * nst + 4) * 8 + 16;
 }
 
 // Preferred cluster size (1, 2 or 4); RAFT_B200_CLUSTER overrides the default of 2.

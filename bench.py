@@ -116,7 +116,7 @@ def oracle_forward_time(n_pairs, steps, warmup):
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
-        return
+        return None
     pps, sec, cores, _ = oracle_forward_time(1, args.steps, args.warmup)
     sample = f'1 pair per step ({H}x{W}, {ITERS} iterations), {args.steps} steps after {args.warmup} warm-up'
     line = {
@@ -128,7 +128,7 @@ def run_reference(args):
         'cpu_baseline': {'value': pps, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': pps, 'unit': 'pairs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
-    print(json.dumps(line), flush=True)
+    return line
 
 
 def run_ours(args):
@@ -322,8 +322,7 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    if line is not None:
-        print(json.dumps(line), flush=True)
+    return line
 
 
 def main():
@@ -335,13 +334,18 @@ def main():
     ap.add_argument('--no-graph', action='store_true', help='launch kernels directly instead of replaying a CUDA graph')
     ap.add_argument('--precision', default=os.environ.get('RAFT_B200_PRECISION', 'f16x2'), choices=['f16x2', 'fp32'])
     args = ap.parse_args()
+    # stdout must carry exactly one JSON line: libraries (NCCL prints its version banner there) get stderr instead
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    # torchrun exports OMP_NUM_THREADS=1; the CPU baseline / reference arm should use the host's cores.  Size the
+    # intra-op pool once, before its first use (resizing a pool that is already in use stalled oneDNN for minutes).
+    torch.set_num_threads(max(1, min(host_cores(), 64)))
     faulthandler.enable()
     faulthandler.dump_traceback_later(420, exit=False)     # a hang leaves stack traces on stderr
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else max(args.warmup, 1)
-    if args.impl == 'reference':
-        run_reference(args)
-    else:
-        run_ours(args)
+    line = run_reference(args) if args.impl == 'reference' else run_ours(args)
+    if line is not None:
+        os.write(real_stdout, (json.dumps(line) + '\n').encode())
 
 
 if __name__ == '__main__':

@@ -107,6 +107,11 @@ static int corr_build_tc(const float* f1, const float* f2, int B, int h, int w, 
     p.b_batch_stride = 1;
     p.mode = EPI_CORR;
     p.corr_div = sqrtf((float)C);
+    {
+      int e = 0;
+      const float m = frexpf(p.corr_div, &e);          // sqrt(C) = m * 2^e; m == 0.5 <=> exact power of two
+      p.corr_mul = (m == 0.5f && p.corr_div * p.corr_div == (float)C) ? 1.0f / p.corr_div : 0.0f;
+    }
     p.out_f32 = pyr[l]; p.f32_stride = N2; p.f32_c0 = 0;
     p.out_scale = 1.0f;
     RAFT_COUNT_LAUNCH();

@@ -40,6 +40,7 @@ constexpr int kTcThreads = 320;           // 1 producer + 1 issuer + 8 promotion
 constexpr int kTileM = 128;
 constexpr int kChunkK = 64;                       // fp16 elements per 128-byte swizzled row
 constexpr int kABytes = kTileM * kChunkK * 2;     // 16 KiB per A plane per stage
+constexpr int kEpiPatchBytes = 8 * 4096;          // EPI_CORR: transposition patches of the 8 epilogue warps
 constexpr int kSmemBudget = 227 * 1024 - 2048;
 
 struct alignas(64) TcConvParams {
@@ -61,6 +62,7 @@ struct alignas(64) TcConvParams {
   const float* inv_scale;         // device scalar: 1 / (2^k weight scale); may be null (=1)
   float out_scale;                // applied after the activation (0.25 for the mask head)
   float corr_div;                 // EPI_CORR: sqrt(C)
+  float corr_mul;                 // EPI_CORR: 1/sqrt(C) when that is an exact power of two (C a power of 4), else 0
   float* out_f32; int f32_stride, f32_c0;
   __half* out_hi; __half* out_lo; int h_stride, h_c0;
   const float* post_scale;        // EPI_LINEAR: optional per-column affine after the bias (folded BatchNorm):
@@ -247,8 +249,42 @@ __device__ __noinline__ void tc_epilogue_chunk(const TcConvParams& pp, float* v,
     }
   }
 }
+// Coalesced store of one 32x32 accumulator block of the correlation volume (patch = swizzled transposition buffer):
+// 8 lanes x 16 bytes cover a row, so a warp writes 4 full 128-byte pyramid rows per instruction.
+__device__ __noinline__ void tc_store_corr_block(const float* patch, long long pix_lane, float* out, int stride, int col0,
+                                                 int ncols_left, int n_total, float corr_mul, float corr_div) {
+  const int lane = threadIdx.x & 31;
+  const int rsub = lane >> 3, q4 = lane & 7;
+  const int col = col0 + 4 * q4;
+#pragma unroll 2
+  for (int i = 0; i < 8; ++i) {
+    const int r = 4 * i + rsub;
+    const long long pl = __shfl_sync(0xffffffffu, pix_lane, r);
+    float4 a4 = *reinterpret_cast<const float4*>(patch + r * 32 + ((q4 ^ (r & 7)) << 2));
+    if (corr_mul != 0.0f) {
+      a4.x *= corr_mul; a4.y *= corr_mul; a4.z *= corr_mul; a4.w *= corr_mul;
+    } else {
+      a4.x = __fdiv_rn(a4.x, corr_div); a4.y = __fdiv_rn(a4.y, corr_div);
+      a4.z = __fdiv_rn(a4.z, corr_div); a4.w = __fdiv_rn(a4.w, corr_div);
+    }
+    if (pl >= 0 && 4 * q4 < ncols_left) {
+      float* dst = out + (size_t)pl * stride + col;
+      if (col + 4 <= n_total && (stride & 3) == 0) {
+        *reinterpret_cast<float4*>(dst) = a4;
+      } else {
+        if (col < n_total) dst[0] = a4.x;
+        if (col + 1 < n_total) dst[1] = a4.y;
+        if (col + 2 < n_total) dst[2] = a4.z;
+        if (col + 3 < n_total) dst[3] = a4.w;
+      }
+    }
+  }
+}
 #endif
 
+// kCorr selects the correlation epilogue at compile time so that its transposition path costs the convolution
+// instantiation neither registers nor code.
+template <bool kCorr>
 __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_constant__ TcConvParams p) {
 #if defined(__CUDA_ARCH__)
   // Persistent: CTA c processes output tiles c, c + gridDim.x, ...  A tile is (pixel tile, column tile).  All
@@ -263,6 +299,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
   uint64_t* acc_full = empty_bar + nst;      // [2] issuer -> promotion warps
   uint64_t* acc_empty = acc_full + 2;        // [2] promotion warps -> issuer
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* patches = reinterpret_cast<float*>(smem + (size_t)nst * p.stage_bytes + 256);   // EPI_CORR only: 8 x 4 KB
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -430,7 +467,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         const int ty = mt % p.tiles_y;
         const int b = mt / p.tiles_y;
         const int x = tx * p.TW + xl, y = ty * p.TH + yl;
-        if (x < p.W && y < p.H) {
+        if constexpr (kCorr) {
+          // Pyramid rows are 128 px * N2 * 4 B apart: written thread-per-row, every store instruction touches 32 lines
+          // with 16 bytes each (measured ~20 us per 128 KB tile).  Transpose each 32x32 block through a swizzled smem
+          // patch instead: 8 lanes x 16 bytes cover one row, a warp writes 4 full 128-byte rows per instruction.
+          float* patch = patches + (warp - 2) * 1024;
+          const long long pix_lane = (x < p.W && y < p.H) ? ((long long)b * p.H + y) * p.W + x : -1;
+#pragma unroll
+          for (int ci = 0; ci < 4; ++ci) {
+            if (ci < my_chunks) {
+              const int c0 = (chunk0 + ci) * 32;
+              __syncwarp();
+#pragma unroll
+              for (int qq = 0; qq < 8; ++qq)
+                *reinterpret_cast<float4*>(patch + lane * 32 + ((qq ^ (lane & 7)) << 2)) =
+                    make_float4(racc[ci][4 * qq], racc[ci][4 * qq + 1], racc[ci][4 * qq + 2], racc[ci][4 * qq + 3]);
+              __syncwarp();
+              tc_store_corr_block(patch, pix_lane, p.out_f32, p.f32_stride, nt * p.bn + c0, p.bn - c0, p.n_total, p.corr_mul,
+                                  p.corr_div);
+            }
+          }
+        } else if (x < p.W && y < p.H) {   // (convolution instantiation)
           const size_t pix = ((size_t)b * p.H + y) * p.W + x;
           __align__(16) float buf32[32];
 #pragma unroll
@@ -477,14 +534,15 @@ inline int tc_finalize(TcConvParams& p) {
   p.tiles_x = ceil_div(p.W, p.TW);
   p.tiles_y = ceil_div(p.H, p.TH);
   p.stage_bytes = 2 * kABytes + 2 * p.bn * kChunkK * 2;
-  int nst = kSmemBudget / p.stage_bytes;
+  const int patch = p.mode == EPI_CORR ? kEpiPatchBytes : 0;
+  int nst = (kSmemBudget - patch) / p.stage_bytes;
   if (nst > 8) nst = 8;
   p.nstages = nst;
   int cols = 32;
   while (cols < 2 * p.bn) cols <<= 1;           // two accumulator buffers (ping-pong promotion)
   p.tmem_cols = cols;
   if (p.group_chunks <= 0) p.group_chunks = 2;
-  return nst * p.stage_bytes + 1024 /*align slack*/ + (2 * nst + 4) * 8 + 16;
+  return nst * p.stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + patch;
 }
 
 // Preferred cluster size (1, 2 or 4); RAFT_B200_CLUSTER overrides the default of 2.
@@ -515,7 +573,8 @@ inline int tc_launch(TcConvParams& p, int n_tiles_n, cudaStream_t stream) {
   if (p.nstages < 2) return RAFT_ERR_UNSUPPORTED;
   static bool attr_set = false;   // benign race: idempotent
   if (!attr_set) {
-    RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   const int mtiles = p.B * p.tiles_y * p.tiles_x;
@@ -523,7 +582,8 @@ inline int tc_launch(TcConvParams& p, int n_tiles_n, cudaStream_t stream) {
   p.cluster = 1;
   const long ntiles = (long)mtiles * n_tiles_n;
   const unsigned grid = (unsigned)(ntiles < kNumSMs ? ntiles : kNumSMs);   // one persistent CTA per SM
-  conv_tc_kernel<<<grid, kTcThreads, smem, stream>>>(p);
+  if (p.mode == EPI_CORR) conv_tc_kernel<true><<<grid, kTcThreads, smem, stream>>>(p);
+  else conv_tc_kernel<false><<<grid, kTcThreads, smem, stream>>>(p);
   return raft_launch_status();
 }
 

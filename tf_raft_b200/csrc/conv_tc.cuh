@@ -36,7 +36,8 @@ enum TcEpilogue : int {
 };
 enum TcAct : int { ACT_NONE = 0, ACT_RELU = 1 };
 
-constexpr int kTcThreads = 320;           // 1 producer + 1 issuer + 8 promotion/epilogue warps
+constexpr int kEpiWarpsConv = 16;         // promotion/epilogue warps of the convolution instantiation (4 per TMEM lane quarter)
+constexpr int kEpiWarpsCorr = 8;          // ... of the correlation instantiation (each needs a 4 KB transposition patch)
 constexpr int kTileM = 128;
 constexpr int kChunkK = 64;                       // fp16 elements per 128-byte swizzled row
 constexpr int kABytes = kTileM * kChunkK * 2;     // 16 KiB per A plane per stage
@@ -284,8 +285,8 @@ __device__ __noinline__ void tc_store_corr_block(const float* patch, long long p
 
 // kCorr selects the correlation epilogue at compile time so that its transposition path costs the convolution
 // instantiation neither registers nor code.
-template <bool kCorr>
-__global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_constant__ TcConvParams p) {
+template <bool kCorr, int kEpiWarps>
+__global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_tc_kernel(const __grid_constant__ TcConvParams p) {
 #if defined(__CUDA_ARCH__)
   // Persistent: CTA c processes output tiles c, c + gridDim.x, ...  A tile is (pixel tile, column tile).  All
   // three roles walk the same tile sequence; the smem ring and the two TMEM buffers carry straight across
@@ -312,7 +313,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
   const int gsz = p.group_chunks;
   const int ngroups = (total + gsz - 1) / gsz;            // promotion groups per tile
   const int nchunks32 = (p.bn + 31) >> 5;                 // 32-column accumulator chunks
-  const int chunks_a = (nchunks32 + 1) >> 1;              // handled by warps 2..5; the rest by warps 6..9
+  constexpr int kParts = kEpiWarps / 4;                   // warps per TMEM lane quarter: each takes a slice of the columns
+  constexpr int kMaxCh = 8 / kParts;                      // accumulator chunks per thread (2 or 4)
+  const int chunks_per_part = (nchunks32 + kParts - 1) / kParts;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < nst; ++s) {
@@ -321,7 +324,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], nchunks32 > 1 ? 8 : 4);    // one arrival per participating warp
+      mbar_init(&acc_empty[i], 4 * ((nchunks32 + chunks_per_part - 1) / chunks_per_part));   // one arrival per participating warp
     }
     fence_mbar_init();
     prefetch_tmap(&p.a_map[0]);
@@ -411,9 +414,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
   } else {
     // ===================== promotion + epilogue (warps 2..9) =====================
     const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;                // 0: chunks [0, chunks_a), 1: chunks [chunks_a, nchunks32)
-    const int chunk0 = half ? chunks_a : 0;
-    const int my_chunks = half ? (nchunks32 - chunks_a) : chunks_a;
+    const int part = (warp - 2) >> 2;                // column slice of this warp within its lane quarter
+    const int chunk0 = part * chunks_per_part;
+    const int my_chunks = max(0, min(chunks_per_part, nchunks32 - chunk0));
     const int m = quarter * 32 + lane;               // tile row == TMEM lane
     const int xl = m % p.TW, yl = m / p.TW;
     const float inv_scale = p.inv_scale ? __ldg(p.inv_scale) : 1.0f;
@@ -422,9 +425,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     if (my_chunks > 0) {
       int gg = 0;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        float racc[4][32];
+        float racc[kMaxCh][32];
 #pragma unroll
-        for (int ci = 0; ci < 4; ++ci)
+        for (int ci = 0; ci < kMaxCh; ++ci)
 #pragma unroll
           for (int j = 0; j < 32; ++j) racc[ci][j] = 0.0f;
 
@@ -434,7 +437,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
           tc_fence_after();
           if (p.dbg && blockIdx.x == 0 && gg < 512 && warp == 2 && lane == 0) p.dbg[1024 + gg] = clock64();   // group retired
 #pragma unroll
-          for (int ci = 0; ci < 4; ++ci) {
+          for (int ci = 0; ci < kMaxCh; ++ci) {
             if (ci < my_chunks) {
               const int c0 = (chunk0 + ci) * 32;
               uint32_t r[32];
@@ -474,7 +477,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
           float* patch = patches + (warp - 2) * 1024;
           const long long pix_lane = (x < p.W && y < p.H) ? ((long long)b * p.H + y) * p.W + x : -1;
 #pragma unroll
-          for (int ci = 0; ci < 4; ++ci) {
+          for (int ci = 0; ci < kMaxCh; ++ci) {
             if (ci < my_chunks) {
               const int c0 = (chunk0 + ci) * 32;
               __syncwarp();
@@ -491,7 +494,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
           const size_t pix = ((size_t)b * p.H + y) * p.W + x;
           __align__(16) float buf32[32];
 #pragma unroll
-          for (int ci = 0; ci < 4; ++ci) {
+          for (int ci = 0; ci < kMaxCh; ++ci) {
             if (ci < my_chunks) {
               const int c0 = (chunk0 + ci) * 32;
 #pragma unroll
@@ -573,8 +576,8 @@ inline int tc_launch(TcConvParams& p, int n_tiles_n, cudaStream_t stream) {
   if (p.nstages < 2) return RAFT_ERR_UNSUPPORTED;
   static bool attr_set = false;   // benign race: idempotent
   if (!attr_set) {
-    RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<false, kEpiWarpsConv>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<true, kEpiWarpsCorr>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   const int mtiles = p.B * p.tiles_y * p.tiles_x;
@@ -582,8 +585,8 @@ inline int tc_launch(TcConvParams& p, int n_tiles_n, cudaStream_t stream) {
   p.cluster = 1;
   const long ntiles = (long)mtiles * n_tiles_n;
   const unsigned grid = (unsigned)(ntiles < kNumSMs ? ntiles : kNumSMs);   // one persistent CTA per SM
-  if (p.mode == EPI_CORR) conv_tc_kernel<true><<<grid, kTcThreads, smem, stream>>>(p);
-  else conv_tc_kernel<false><<<grid, kTcThreads, smem, stream>>>(p);
+  if (p.mode == EPI_CORR) conv_tc_kernel<true, kEpiWarpsCorr><<<grid, 64 + 32 * kEpiWarpsCorr, smem, stream>>>(p);
+  else conv_tc_kernel<false, kEpiWarpsConv><<<grid, 64 + 32 * kEpiWarpsConv, smem, stream>>>(p);
   return raft_launch_status();
 }
 

@@ -105,7 +105,7 @@ inline EncWs enc_ws_layout(void* base, int variant, int N, int H, int W) {
     const size_t np1 = (size_t)N * ((H + 1) / 2) * ((W + 1) / 2);
     E.Ih = (__half*)take(np1 * 192 * 2); E.Il = (__half*)take(np1 * 192 * 2);
   }
-  E.part = (float*)take((size_t)N * kNormSplit * 256 * 4);
+  E.part = (float*)take((size_t)N * kNormSplit * 3 * 256 * 4);
   E.mean = (float*)take((size_t)N * 256 * 4);
   E.mult = (float*)take((size_t)N * 256 * 4);
   E.total = off;
@@ -189,19 +189,17 @@ struct EncCtx {
 
 // y (npix, C) raw conv output -> normalised, activated, (+skip), re-split.
 inline int enc_norm_apply(const EncCtx& c, const EncNormSlot& ns, const float* y, size_t npix, int P, int relu,
-                          const float* skip, float* out32, __half* hi, __half* lo) {
+                          const float* skip32, const __half* skip_hi, const __half* skip_lo, float* out32, __half* hi,
+                          __half* lo) {
   const int C = ns.C, G = c.per_image ? c.N : 1;
   const int Pg = c.per_image ? P : (int)npix;
   const float* gamma = reinterpret_cast<const float*>(c.prep + ns.gamma);
   const float* beta = reinterpret_cast<const float*>(c.prep + ns.beta);
-  for (int pass = 0; pass < 2; ++pass) {
-    norm_partial_kernel<<<dim3((unsigned)G, kNormSplit), 256, 0, c.st>>>(y, Pg, C, kNormSplit, c.W.mean, pass, c.W.part);
-    norm_final_kernel<<<ceil_div(G * C, 128), 128, 0, c.st>>>(c.W.part, G, C, kNormSplit, Pg, pass, gamma, 1e-3f,
-                                                            pass ? c.W.mult : c.W.mean);
-  }
-  norm_apply_kernel<<<grid_for(npix * pad64(C)), 256, 0, c.st>>>(y, npix, P, C, c.per_image, c.W.mean, c.W.mult, beta, relu,
-                                                                 skip, out32, hi, lo, pad64(C));
-  g_launches += 5;
+  norm_stats_kernel<<<dim3((unsigned)G, kNormSplit), 256, 0, c.st>>>(y, Pg, C, kNormSplit, c.W.part);
+  norm_final_kernel<<<ceil_div(G * C * 32, 256), 256, 0, c.st>>>(c.W.part, G, C, kNormSplit, gamma, 1e-3f, c.W.mean, c.W.mult);
+  norm_apply_kernel<<<grid_for(npix * (pad64(C) / 8)), 256, 0, c.st>>>(y, npix, P, C, c.per_image, c.W.mean, c.W.mult, beta, relu,
+                                                                 skip32, skip_hi, skip_lo, out32, hi, lo, pad64(C));
+  g_launches += 3;
   return raft_launch_status();
 }
 
@@ -278,7 +276,7 @@ inline int encoder_forward(int variant, int norm_type, int out_dim, const void* 
       RAFT_CUDA_TRY(cudaMemsetAsync(E.Xl, 0, npix * pad64(S.c0) * 2, st));
     }
     RAFT_TRY(enc_conv_tc(c, L.conv1, &L.norm1, E.Ih, E.Il, h, w, h, w, 1, 1, nullptr, c.stats ? E.Y32 : E.X32, E.Xh, E.Xl));
-    if (c.stats) RAFT_TRY(enc_norm_apply(c, L.norm1, E.Y32, npix, h * w, 1, nullptr, E.X32, E.Xh, E.Xl));
+    if (c.stats) RAFT_TRY(enc_norm_apply(c, L.norm1, E.Y32, npix, h * w, 1, nullptr, nullptr, nullptr, nullptr, E.Xh, E.Xl));
   }
 
   float *X32 = E.X32, *O32 = E.O32;
@@ -297,17 +295,20 @@ inline int encoder_forward(int variant, int norm_type, int out_dim, const void* 
       RAFT_CUDA_TRY(cudaMemsetAsync(Ol, 0, npo * pad64(cc) * 2, st));
     }
     RAFT_TRY(enc_conv_tc(c, L.bc1[k], &L.bn1[k], Xh, Xl, h, w, ho, wo, st2, 1, nullptr, c.stats ? E.Y32 : nullptr, E.Fh, E.Fl));
-    if (c.stats) RAFT_TRY(enc_norm_apply(c, L.bn1[k], E.Y32, npo, ho * wo, 1, nullptr, nullptr, E.Fh, E.Fl));
+    if (c.stats) RAFT_TRY(enc_norm_apply(c, L.bn1[k], E.Y32, npo, ho * wo, 1, nullptr, nullptr, nullptr, nullptr, E.Fh, E.Fl));
     // skip branch
     const float* skip = X32;
     if (L.has_ds[k]) {
       RAFT_TRY(enc_conv_tc(c, L.bds[k], &L.bnd[k], Xh, Xl, h, w, ho, wo, st2, 0, nullptr, c.stats ? E.Y32 : E.D32, nullptr, nullptr));
-      if (c.stats) RAFT_TRY(enc_norm_apply(c, L.bnd[k], E.Y32, npo, ho * wo, 0, nullptr, E.D32, nullptr, nullptr));
+      if (c.stats) RAFT_TRY(enc_norm_apply(c, L.bnd[k], E.Y32, npo, ho * wo, 0, nullptr, nullptr, nullptr, E.D32, nullptr, nullptr));
       skip = E.D32;
     }
     // conv2 + norm2 + relu, then relu(skip + fx) -> O
     RAFT_TRY(enc_conv_tc(c, L.bc2[k], &L.bn2[k], E.Fh, E.Fl, ho, wo, ho, wo, 1, 1, skip, c.stats ? E.Y32 : O32, Oh, Ol));
-    if (c.stats) RAFT_TRY(enc_norm_apply(c, L.bn2[k], E.Y32, npo, ho * wo, 1, skip, O32, Oh, Ol));
+    if (c.stats) {   // skip = block input: from D32 after a downsample, else from the block's own fp16 operand planes
+      if (L.has_ds[k]) RAFT_TRY(enc_norm_apply(c, L.bn2[k], E.Y32, npo, ho * wo, 1, E.D32, nullptr, nullptr, nullptr, Oh, Ol));
+      else RAFT_TRY(enc_norm_apply(c, L.bn2[k], E.Y32, npo, ho * wo, 1, nullptr, Xh, Xl, nullptr, Oh, Ol));
+    }
     // next block reads O
     float* t32 = X32; X32 = O32; O32 = t32;
     __half* th_ = Xh; Xh = Oh; Oh = th_;

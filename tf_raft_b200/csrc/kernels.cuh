@@ -503,70 +503,138 @@ __global__ void pack_weights_kernel(const PackParams p) {
 // ------------------------------------------------------------------------------------------------
 // Normalisation layers of the encoders (extractor.py:6-16): tfa InstanceNormalization (statistics per
 // image) / Keras BatchNormalization in training mode (statistics over the batch), eps = 1e-3.
-// y is the raw convolution output (G groups x P pixels x C channels, fp32).  Two deterministic
-// passes: mean, then sum of squared deviations (no E[x^2]-E[x]^2 cancellation).
-//   pass = 0: part[g][split][c] = sum_p y            pass = 1: part[...] = sum_p (y - mean[g][c])^2
+// y is the raw convolution output (G groups x P pixels x C channels, fp32).  ONE pass over y:
+// every thread accumulates shifted sums of its pixels (shift = its first sample, so there is no
+// E[x^2]-E[x]^2 cancellation), partial (n, mean, M2) triples are merged with Chan's formula in a fixed
+// order (deterministic).   part[g][split][{n, mean, M2}][c]
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) norm_partial_kernel(const float* __restrict__ y, int P, int C, int nsplit,
-                                                           const float* __restrict__ mean, int pass,
-                                                           float* __restrict__ part) {
-  __shared__ float red[256];
+__device__ __forceinline__ void chan_merge(float& na, float& ma, float& m2a, float nb, float mb, float m2b) {
+  if (nb == 0.f) return;
+  const float n = na + nb, d = mb - ma;
+  ma = ma + d * (nb / n);
+  m2a = m2a + m2b + d * d * (na * nb / n);
+  na = n;
+}
+__global__ void __launch_bounds__(256) norm_stats_kernel(const float* __restrict__ y, int P, int C, int nsplit,
+                                                         float* __restrict__ part) {
+  __shared__ float red[3][256];
   const int g = blockIdx.x, sp = blockIdx.y;
   const int lanes = 256 / C > 0 ? 256 / C : 1;          // pixel lanes per block (C <= 256)
   const int c = threadIdx.x % C, pl = threadIdx.x / C;
   const int per = (P + nsplit - 1) / nsplit;
   const int p0 = sp * per, p1 = min(P, p0 + per);
-  float acc = 0.f;
-  if (pl < lanes) {
-    const float mu = pass ? mean[(size_t)g * C + c] : 0.f;
+  float n = 0.f, mean = 0.f, m2 = 0.f;
+  if (pl < lanes && p0 + pl < p1) {
     const float* base = y + ((size_t)g * P) * C + c;
+    const float K = base[(size_t)(p0 + pl) * C];
+    float s1 = 0.f, s2 = 0.f;
     for (int px = p0 + pl; px < p1; px += lanes) {
-      const float v = base[(size_t)px * C] - mu;
-      acc += pass ? v * v : v;
+      const float v = base[(size_t)px * C] - K;
+      s1 += v;
+      s2 += v * v;
+      n += 1.f;
     }
+    mean = K + s1 / n;
+    m2 = fmaxf(s2 - s1 * s1 / n, 0.f);
   }
-  red[threadIdx.x] = acc;
+  red[0][threadIdx.x] = n; red[1][threadIdx.x] = mean; red[2][threadIdx.x] = m2;
   __syncthreads();
   if (pl == 0) {
-    float tot = 0.f;
-    for (int l = 0; l < lanes; ++l) tot += red[l * C + c];      // fixed order: deterministic
-    part[((size_t)g * nsplit + sp) * C + c] = tot;
+    for (int l = 1; l < lanes; ++l) chan_merge(n, mean, m2, red[0][l * C + c], red[1][l * C + c], red[2][l * C + c]);
+    float* o = part + (((size_t)g * nsplit + sp) * 3) * C + c;
+    o[0] = n; o[C] = mean; o[2 * C] = m2;
   }
 }
-// pass 0: mean = sum/P.   pass 1: a = rsqrt(sum/P + eps) * gamma   (the multiplier applied to (y - mean)).
-__global__ void norm_final_kernel(const float* __restrict__ part, int G, int C, int nsplit, int P, int pass,
-                                  const float* __restrict__ gamma, float eps, float* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// mean[g][c] and mult[g][c] = rsqrt(var + eps) * gamma[c]  (the multiplier applied to (y - mean)).
+// One warp per (g, c): lanes merge their partials, then a fixed xor-shuffle tree (deterministic).
+__global__ void norm_final_kernel(const float* __restrict__ part, int G, int C, int nsplit,
+                                  const float* __restrict__ gamma, float eps, float* __restrict__ mean_out,
+                                  float* __restrict__ mult_out) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= G * C) return;
   const int g = i / C, c = i % C;
-  float tot = 0.f;
-  for (int s = 0; s < nsplit; ++s) tot += part[((size_t)g * nsplit + s) * C + c];
-  out[i] = pass ? rsqrtf(tot / (float)P + eps) * gamma[c] : tot / (float)P;
+  float n = 0.f, mean = 0.f, m2 = 0.f;
+  for (int s = lane; s < nsplit; s += 32) {
+    const float* o = part + (((size_t)g * nsplit + s) * 3) * C + c;
+    chan_merge(n, mean, m2, o[0], o[C], o[2 * C]);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const float nb = __shfl_xor_sync(0xffffffffu, n, off), mb = __shfl_xor_sync(0xffffffffu, mean, off),
+                m2b = __shfl_xor_sync(0xffffffffu, m2, off);
+    // both partners compute the same merged triple (merge in lane order so the result is bitwise identical)
+    float na = n, ma = mean, m2a = m2;
+    if (lane & off) { na = nb; ma = mb; m2a = m2b; chan_merge(na, ma, m2a, n, mean, m2); }
+    else chan_merge(na, ma, m2a, nb, mb, m2b);
+    n = na; mean = ma; m2 = m2a;
+  }
+  if (lane == 0) {
+    mean_out[i] = mean;
+    mult_out[i] = rsqrtf(m2 / n + eps) * gamma[c];
+  }
 }
 // out = [relu]((y - mean) * a + beta);  optional skip: out = relu(skip + out)  (ResBlock, extractor.py:41-49)
-// Writes fp32 (optional) and the fp16 hi/lo operand planes (optional; channels [C, c_pad) zeroed).
+// skip comes either as an fp32 plane (skip32, C channels) or as the fp16 hi/lo operand planes of the block input
+// (skip_hi/lo, c_pad channels; hi + lo reproduces the fp32 value to 2^-23).  Writes fp32 (optional) and the fp16
+// hi/lo operand planes (optional; channels [C, c_pad) zeroed).  One thread = 8 consecutive channels (C % 8 == 0).
 __global__ void norm_apply_kernel(const float* __restrict__ y, size_t npix, int P, int C, int per_image,
                                   const float* __restrict__ mean, const float* __restrict__ a,
-                                  const float* __restrict__ beta, int relu, const float* __restrict__ skip,
+                                  const float* __restrict__ beta, int relu, const float* __restrict__ skip32,
+                                  const __half* __restrict__ skip_hi, const __half* __restrict__ skip_lo,
                                   float* __restrict__ out32, __half* __restrict__ hi, __half* __restrict__ lo,
                                   int c_pad) {
-  const size_t total = npix * (size_t)c_pad;
+  const int gpp = c_pad >> 3;                                    // 8-channel groups per pixel
+  const size_t total = npix * (size_t)gpp;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t px = i / c_pad;
-    const int c = (int)(i - px * c_pad);
-    float v = 0.f;
+    const size_t px = i / gpp;
+    const int c = (int)(i - px * gpp) << 3;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (c < C) {
       const size_t g = per_image ? px / P : 0;
-      v = (y[px * C + c] - mean[g * C + c]) * a[g * C + c] + beta[c];
-      if (relu) v = fmaxf(v, 0.f);
-      if (skip) v = fmaxf(skip[px * C + c] + v, 0.f);
-      if (out32) out32[px * C + c] = v;
+      const float* yp = y + px * C + c;
+      const float* mp = mean + g * C + c;
+      const float* ap = a + g * C + c;
+      const float* bp = beta + c;
+      float4 t[2] = {*reinterpret_cast<const float4*>(yp), *reinterpret_cast<const float4*>(yp + 4)};
+      const float yy[8] = {t[0].x, t[0].y, t[0].z, t[0].w, t[1].x, t[1].y, t[1].z, t[1].w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        v[e] = (yy[e] - __ldg(mp + e)) * __ldg(ap + e) + __ldg(bp + e);
+        if (relu) v[e] = fmaxf(v[e], 0.f);
+      }
+      if (skip32) {
+        const float4 s0 = *reinterpret_cast<const float4*>(skip32 + px * C + c), s1 = *reinterpret_cast<const float4*>(skip32 + px * C + c + 4);
+        const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = fmaxf(ss[e] + v[e], 0.f);
+      } else if (skip_hi) {
+        const uint4 h4 = *reinterpret_cast<const uint4*>(skip_hi + px * c_pad + c), l4 = *reinterpret_cast<const uint4*>(skip_lo + px * c_pad + c);
+        const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
+          const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[e]));
+          v[2 * e] = fmaxf(hf.x + lf.x + v[2 * e], 0.f);
+          v[2 * e + 1] = fmaxf(hf.y + lf.y + v[2 * e + 1], 0.f);
+        }
+      }
+      if (out32) {
+        *reinterpret_cast<float4*>(out32 + px * C + c) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(out32 + px * C + c + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      }
     }
     if (hi) {
-      __half hh, ll;
-      split_f16(v, hh, ll);
-      hi[i] = hh;
-      lo[i] = ll;
+      uint32_t ph[4], pl[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        __half h0, l0, h1, l1;
+        split_f16(v[2 * e], h0, l0);
+        split_f16(v[2 * e + 1], h1, l1);
+        ph[e] = pack_h2(h0, h1);
+        pl[e] = pack_h2(l0, l1);
+      }
+      *reinterpret_cast<uint4*>(hi + px * c_pad + c) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+      *reinterpret_cast<uint4*>(lo + px * c_pad + c) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
     }
   }
 }

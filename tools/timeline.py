@@ -31,4 +31,4 @@ for g in range(min(n_g, 10)):
     print(f'{g:5d} {t[2][g]-t0:9d} {t[3][g]-t0:9d} {t[3][g]-t[2][g]:10d} {gap:12d}')
 d = np.diff(t[1][:n_it]); print('landed-to-landed per chunk: median', int(np.median(d)), 'mean', int(d.mean()))
 print('load latency (landed - slot_free): median', int(np.median(t[1][:n_it] - t[0][:n_it])))
-print('total mainloop cycles', int(t[3][n_g-1] - t0))
+print('total mainloop cycles', int(t[3][n_g-1] - t0), '| epilogue cycles (last drain -> tile done)', int(t[3][511] - t[3][n_g-1]))

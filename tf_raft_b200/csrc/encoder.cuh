@@ -268,8 +268,15 @@ inline int encoder_forward(int variant, int norm_type, int out_dim, const void* 
   {
     const size_t npix = (size_t)N * h * w;
     const int tot_h = (h - 1) * 2 + 7 - H, tot_w = (w - 1) * 2 + 7 - W;
-    stem_im2col_kernel<<<grid_for(npix * 24), 256, 0, st>>>(images, N, H, W, h, w, (tot_h > 0 ? tot_h : 0) / 2,
-                                                            (tot_w > 0 ? tot_w : 0) / 2, image_norm, E.Ih, E.Il);
+    const float* src = images;
+    if (image_norm) {                                 // normalise once (O32 is free until the first ResBlock finishes)
+      const size_t nimg = (size_t)N * H * W * 3;
+      image_norm_kernel<<<grid_for(nimg), 256, 0, st>>>(images, E.O32, nimg);
+      ++g_launches;
+      src = E.O32;
+    }
+    stem_im2col_kernel<<<grid_for(npix * 24), 256, 0, st>>>(src, N, H, W, h, w, (tot_h > 0 ? tot_h : 0) / 2,
+                                                            (tot_w > 0 ? tot_w : 0) / 2, 0, E.Ih, E.Il);
     ++g_launches;
     if (!c.stats && pad64(S.c0) != S.c0) {
       RAFT_CUDA_TRY(cudaMemsetAsync(E.Xh, 0, npix * pad64(S.c0) * 2, st));

@@ -113,6 +113,7 @@ struct LookupParams {
 };
 
 __global__ void __launch_bounds__(256) corr_lookup_kernel(const LookupParams p) {
+  __shared__ float4 axis_smem[8 * 32];                          // per warp: 16 x-axis + 16 y-axis tap set-ups
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int side = 2 * p.radius + 1, ntap = side * side;
@@ -125,19 +126,37 @@ __global__ void __launch_bounds__(256) corr_lookup_kernel(const LookupParams p) 
     const float inv = 1.0f / (float)(1 << l);                    // exact power of two
     const float cx = __fmul_rn(__ldg(p.coords + 2 * (size_t)q), inv);     // coords / 2**i  (corr.py:141)
     const float cy = __fmul_rn(__ldg(p.coords + 2 * (size_t)q + 1), inv);
-    // All gathers of this (query, level) are issued before any is consumed: the lookup is latency-bound
-    // (dependent DRAM/L2 gathers), so memory-level parallelism -- 12 loads in flight per lane -- is what counts.
+    // The x-part of a tap depends only on a, the y-part only on b: the 2*(2r+1) axis set-ups (clamp, floor, ceil,
+    // weights, indices -- corr.py:40-60) are computed once per (query, level) by lanes 0..2*side-1 and shared through
+    // shared memory; each tap then only multiplies weights and adds indices -- the same fp32 operations in the same
+    // order as the per-tap evaluation, so results stay bit-identical.  All gathers are issued before any is consumed
+    // (the kernel is latency / instruction bound, not bandwidth bound).
     constexpr int kMaxIter = 3;                                  // (2r+1)^2 <= 96, i.e. radius <= 4
-    if (ntap <= 32 * kMaxIter) {
+    if (ntap <= 32 * kMaxIter && side <= 16) {
+      float4* ax = axis_smem + (threadIdx.x >> 5) * 32;          // [0,16): x set-ups, [16,32): y set-ups
+      __syncwarp();
+      if (lane < 2 * side) {
+        const bool isy = lane >= side;
+        const int i = isy ? lane - side : lane;
+        const float cc = isy ? cy : cx;
+        const int dim = isy ? H : W;
+        const float g = fminf(fmaxf(__fadd_rn(cc, (float)(i - p.radius)), 0.0f), (float)(dim - 1));   // centroid + delta, clamp
+        const float g0 = floorf(g), g1 = ceilf(g);
+        ax[(isy ? 16 : 0) + i] = make_float4(__fsub_rn(g1, g), __fsub_rn(g, g0), __int_as_float((int)g0), __int_as_float((int)g1));
+      }
+      __syncwarp();
       TapGather tg[kMaxIter];
       float x00[kMaxIter], x01[kMaxIter], x10[kMaxIter], x11[kMaxIter];
 #pragma unroll
       for (int i = 0; i < kMaxIter; ++i) {
         const int t = min(lane + 32 * i, ntap - 1);
         const int a = t / side, b2 = t - a * side;
-        tg[i] = tap_setup(H, W, __fadd_rn(cx, (float)(a - p.radius)), __fadd_rn(cy, (float)(b2 - p.radius)));
-        x00[i] = __ldg(img + tg[i].o00); x01[i] = __ldg(img + tg[i].o01);
-        x10[i] = __ldg(img + tg[i].o10); x11[i] = __ldg(img + tg[i].o11);
+        const float4 sx = ax[a], sy = ax[16 + b2];               // (w1, w0, i0, i1) per axis
+        const int ix0 = __float_as_int(sx.z), ix1 = __float_as_int(sx.w), iy0 = __float_as_int(sy.z), iy1 = __float_as_int(sy.w);
+        tg[i].c00 = __fmul_rn(sy.x, sx.x); tg[i].c01 = __fmul_rn(sy.x, sx.y);
+        tg[i].c10 = __fmul_rn(sy.y, sx.x); tg[i].c11 = __fmul_rn(sy.y, sx.y);
+        x00[i] = __ldg(img + iy0 * W + ix0); x01[i] = __ldg(img + iy0 * W + ix1);
+        x10[i] = __ldg(img + iy1 * W + ix0); x11[i] = __ldg(img + iy1 * W + ix1);
       }
 #pragma unroll
       for (int i = 0; i < kMaxIter; ++i) {
@@ -638,6 +657,13 @@ __global__ void norm_apply_kernel(const float* __restrict__ y, size_t npix, int 
     }
   }
 }
+// model.py:70-71: x -> 2*(x/255)-1, elementwise (each input value is normalised once here instead of once per
+// 7x7 window position in the im2col gather).
+__global__ void image_norm_kernel(const float* __restrict__ img, float* __restrict__ out, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = __fsub_rn(__fmul_rn(2.0f, __fdiv_rn(img[i], 255.0f)), 1.0f);
+}
+
 // Stem im2col (extractor.py:95, model.py:70-71): for every output pixel of the 7x7 stride-2 'same' convolution,
 // the 147 input values (tap-major, then rgb) of its window, normalised 2*(x/255)-1, zero outside the image
 // (padding applies to the normalised image), as fp16 hi/lo planes with 192 channels (147..191 = 0).

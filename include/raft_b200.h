@@ -194,6 +194,13 @@ int raft_b200_encoder_forward(int variant, int norm_type, int out_dim, const voi
 int raft_b200_context_split(const float* cnet, int npix, int hidden, int context, float* net, float* inp,
                             void* stream);
 
+/* One keras Conv2D(cout, (kh, kw), 1, 'same') + optional activation on its own (fp32 FFMA path): the building block
+ * behind the stand-alone FlowHead / ConvGRU / SepConvGRU / *MotionEncoder layers of update.py:5-106 when they are
+ * used outside the fused update block.  x (B,H,W,cin), kernel HWIO, out (B,H,W,out_stride) written at channel out_c0.
+ * act: 0 none, 1 relu, 2 sigmoid, 3 tanh.                                                                        */
+int raft_b200_conv2d(const float* x, const float* kernel, const float* bias, int B, int H, int W, int cin, int kh,
+                     int kw, int cout, int act, float* out, int out_stride, int out_c0, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Model loop  (tf_raft/model.py)
  * ------------------------------------------------------------------------------------------- */

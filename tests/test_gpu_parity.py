@@ -261,3 +261,47 @@ def test_corr_pyramid_full_size_properties(T, precision):
     # iteration-0 lookup: level 0 is all zeros, the rest is not
     out = a.retrieve(T.coords_grid(1, 56, 64))
     assert torch.all(out[..., :81] == 0) and out[..., 81:].abs().max() > 0
+
+
+# --------------------------------------------------------------------------------------------- stand-alone layers
+def test_standalone_update_layers_vs_oracle(T):
+    """FlowHead / ConvGRU / SepConvGRU / motion encoders (update.py:5-106) instantiated on their own."""
+    from tf_raft_b200.layers import BasicMotionEncoder, ConvGRU, FlowHead, SepConvGRU, SmallMotionEncoder
+    rng = np.random.default_rng(31)
+    b, h, w = 2, 9, 11
+    nchw = lambda a: torch.from_numpy(a).permute(0, 3, 1, 2)
+    nhwc = lambda t: t.permute(0, 2, 3, 1).numpy()
+    for variant, hid, xin, corr_ch, Gru, Enc, gname, ename in (('raft', 128, 256, 324, SepConvGRU, BasicMotionEncoder, 'gru', 'encoder'),
+                                                               ('small', 96, 146, 196, ConvGRU, SmallMotionEncoder, 'gru', 'encoder')):
+        p = weights.init_params(variant, 5, bias_scale=0.05)
+        ops = rt.Ops(p)
+        hh = np.tanh(rng.standard_normal((b, h, w, hid))).astype(np.float32)
+        xx = rng.standard_normal((b, h, w, xin)).astype(np.float32)
+        flow = (rng.standard_normal((b, h, w, 2)) * 3).astype(np.float32)
+        corr = rng.standard_normal((b, h, w, corr_ch)).astype(np.float32)
+        gru = Gru(filters=hid)
+        gru.load_params(p, 'update_block.gru.')
+        want = (rt.sep_conv_gru if variant == 'raft' else rt.conv_gru)(ops, nchw(hh), nchw(xx), 'update_block.gru')
+        np.testing.assert_allclose(gru([dev(hh), dev(xx)]).cpu().numpy(), nhwc(want), atol=2e-5, rtol=1e-4)
+        enc = Enc()
+        enc.load_params(p, 'update_block.encoder.')
+        want = (rt.basic_motion_encoder if variant == 'raft' else rt.small_motion_encoder)(ops, nchw(flow), nchw(corr), 'update_block.encoder')
+        np.testing.assert_allclose(enc([dev(flow), dev(corr)]).cpu().numpy(), nhwc(want), atol=5e-5, rtol=1e-4)
+        fh = FlowHead(filters=256 if variant == 'raft' else 128, in_channels=hid)
+        fh.load_params(p, 'update_block.flow_head.')
+        want = rt.flow_head(ops, nchw(hh), 'update_block.flow_head')
+        np.testing.assert_allclose(fh(dev(hh)).cpu().numpy(), nhwc(want), atol=2e-5, rtol=1e-4)
+
+
+@pytest.mark.parametrize('variant,shape,iters', [('raft', (448, 1024), 3), ('small', (128, 256), 4), ('raft', (72, 200), 3)])
+def test_other_resolutions_vs_oracle(T, variant, shape, iters):
+    """BASELINE.json configs[2] geometry (436x1024 crop-or-padded to 448x1024: 128-wide feature rows -> 1x128 tiles), a
+    larger SmallRAFT, and a width that is not a multiple of the tile (25 feature columns)."""
+    H, W = shape
+    p = weights.init_params(variant, 77, bias_scale=0.02, norm_jitter=0.05)
+    im1, im2 = cases.images(1, H, W, 11, 12)
+    want = rt.forward(p, im1, im2, variant, iters)
+    got = _run_model(T, variant, 'f16x2', p, im1, im2, iters)
+    for i in range(iters):
+        err = float((got[i].cpu() - want[i]).abs().max())
+        assert err <= 1e-3, f'{variant} {H}x{W} iteration {i}: max-abs {err}'

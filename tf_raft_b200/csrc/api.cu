@@ -656,6 +656,26 @@ int raft_b200_context_split(const float* cnet, int npix, int hidden, int context
   return raft_launch_status();
 }
 
+int raft_b200_conv2d(const float* x, const float* kernel, const float* bias, int B, int H, int W, int cin, int kh,
+                     int kw, int cout, int act, float* out, int out_stride, int out_c0, void* stream) {
+  if (!x || !kernel || !out) return RAFT_ERR_BAD_ARG;
+  RAFT_TRY(check_dims(B, H, W));
+  if (cin < 1 || cout < 1 || kh < 1 || kw < 1 || !(kh & 1) || !(kw & 1) || act < 0 || act > 3) return RAFT_ERR_BAD_SHAPE;
+  if (out_stride < out_c0 + cout) return RAFT_ERR_BAD_SHAPE;
+  SimtConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.src[0] = x; p.src_stride[0] = cin; p.src_c0[0] = 0; p.src_n[0] = cin; p.nsrc = 1;
+  p.w = kernel; p.bias = bias;
+  p.kh = kh; p.kw = kw; p.cin = cin; p.cout = cout;
+  p.B = B; p.H = H; p.W = W;
+  p.out = out; p.out_stride = out_stride; p.out_c0 = out_c0;
+  p.act = act; p.out_scale = 1.0f;
+  dim3 grid((unsigned)ceil_div(B * H * W, 64), (unsigned)ceil_div(cout, 64));
+  conv_simt_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  RAFT_COUNT_LAUNCH();
+  return raft_launch_status();
+}
+
 int raft_b200_forward_loop(int variant, const void* prepared, const float* const pyr[], int levels, int radius,
                            float* net, const float* inp, float* coords1, float* const flow_up[], int iters, int B,
                            int h, int w, void* workspace, size_t workspace_bytes, int precision, void* stream) {

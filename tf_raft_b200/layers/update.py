@@ -2,9 +2,10 @@
 
 `BasicUpdateBlock(filters=128)([net, inp, corr, flow]) -> (net, 0.25*mask, delta_flow)` and
 `SmallUpdateBlock(filters=96)(...) -> (net, None, delta_flow)` keep the reference's list-of-4 in /
-tuple-of-3 out contract (update.py:118-125, 143-153).  The motion encoder, (Sep)ConvGRU, flow head
-and mask head are not separate Python layers here: they are one launch sequence inside
-libraft_b200.so (raft_b200_update_basic / raft_b200_update_small).
+tuple-of-3 out contract (update.py:118-125, 143-153).  Inside the blocks the motion encoder, (Sep)ConvGRU,
+flow head and mask head are one launch sequence in libraft_b200.so (raft_b200_update_basic /
+raft_b200_update_small); `FlowHead`, `ConvGRU`, `SepConvGRU`, `SmallMotionEncoder`, `BasicMotionEncoder`
+are also provided as stand-alone layers (bottom of this file) for code that builds them one by one.
 
 Parameters live in `self.params`, keyed by the reference's Keras attribute paths relative to the
 block ('encoder.convc1.kernel', 'gru.convz1.bias', 'flow_head.conv1.kernel', 'mask.0.kernel', ...),
@@ -163,3 +164,112 @@ class SmallUpdateBlock(_UpdateBlock):
                 _lib.ptr(net_out), _lib.ptr(delta), b, h, w, _lib.ptr(ws), ws.numel(), self.precision,
                 _lib.stream()), 'update_small')
         return net_out, None, delta
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Stand-alone layers of update.py.  Inside RAFT they are fused into the update-block launch sequence above; these
+# classes exist so that code which instantiates the reference's layers one by one keeps working.  Each Conv2D is one
+# raft_b200_conv2d call (fp32 FFMA kernel); gating is elementwise on the same stream.
+# ----------------------------------------------------------------------------------------------------------
+_ACT = {None: 0, 'relu': 1, 'sigmoid': 2, 'tanh': 3}
+
+
+class _ConvLayers:
+    _spec = ()          # (name, kh, kw, cin, cout)
+
+    def __init__(self, *, device=None, seed=None):
+        self.device = torch.device('cuda' if device is None else device)
+        gen = torch.Generator(device='cpu')
+        gen.manual_seed(0 if seed is None else seed)
+        self.params = {}
+        for name, kh, kw, cin, cout in self._spec:
+            self.params[name + '.kernel'] = glorot_uniform_(torch.empty(kh, kw, cin, cout), gen).to(self.device)
+            self.params[name + '.bias'] = torch.zeros(cout, device=self.device)
+
+    def load_params(self, params, prefix=''):
+        for name in self.params:
+            src = torch.as_tensor(params[prefix + name], dtype=torch.float32)
+            if tuple(src.shape) != tuple(self.params[name].shape):
+                raise ValueError(f'{prefix + name}: expected {tuple(self.params[name].shape)}, got {tuple(src.shape)}')
+            self.params[name] = src.to(self.device).contiguous()
+
+    def _conv(self, x, name, act=None, out=None, out_c0=0):
+        x = _lib.f32c(x)
+        k, b = self.params[name + '.kernel'], self.params[name + '.bias']
+        kh, kw, cin, cout = k.shape
+        bsz, h, w, c = x.shape
+        if c != cin:
+            raise ValueError(f'{name}: expected {cin} input channels, got {c}')
+        if out is None:
+            out = torch.empty((bsz, h, w, cout), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().raft_b200_conv2d(_lib.ptr(x), _lib.ptr(k), _lib.ptr(b), bsz, h, w, cin, kh, kw, cout,
+                                                   _ACT[act], _lib.ptr(out), out.shape[-1], out_c0, _lib.stream()), 'conv2d')
+        return out
+
+
+class FlowHead(_ConvLayers):
+    """Reference update.py:5-14: conv2(relu(conv1(x))), 3x3 convolutions, 2 output channels."""
+
+    def __init__(self, filters=256, in_channels=128, **kw):
+        self.filters = filters
+        self._spec = (('conv1', 3, 3, in_channels, filters), ('conv2', 3, 3, filters, 2))
+        super().__init__(**kw)
+
+    def __call__(self, inputs):
+        return self._conv(self._conv(inputs, 'conv1', 'relu'), 'conv2')
+
+
+class ConvGRU(_ConvLayers):
+    """Reference update.py:17-35: 3x3 ConvGRU on [h, x]."""
+    _taps = (('', 3, 3),)
+
+    def __init__(self, filters=128, in_channels=None, **kw):
+        self.filters = filters
+        cin = filters + (in_channels if in_channels is not None else {96: 146, 128: 256}.get(filters, filters))
+        self._spec = tuple((f'conv{g}{sfx}', kh, kwd, cin, filters) for sfx, kh, kwd in self._taps for g in 'zrq')
+        super().__init__(**kw)
+
+    def _step(self, h, x, sfx):
+        hx = torch.cat([h, x], dim=-1)
+        z = self._conv(hx, 'convz' + sfx, 'sigmoid')
+        r = self._conv(hx, 'convr' + sfx, 'sigmoid')
+        q = self._conv(torch.cat([r * h, x], dim=-1), 'convq' + sfx, 'tanh')
+        return (1 - z) * h + z * q
+
+    def __call__(self, inputs):
+        h, x = inputs
+        h, x = _lib.f32c(h), _lib.f32c(x)
+        for sfx, _, _ in self._taps:
+            h = self._step(h, x, sfx)
+        return h
+
+
+class SepConvGRU(ConvGRU):
+    """Reference update.py:38-67: horizontal (1x5) then vertical (5x1) gated update."""
+    _taps = (('1', 1, 5), ('2', 5, 1))
+
+
+class SmallMotionEncoder(_ConvLayers):
+    """Reference update.py:70-85 -> concat([conv(...), flow]) with 82 channels."""
+    _spec = (('convc1', 1, 1, 196, 96), ('convf1', 7, 7, 2, 64), ('convf2', 3, 3, 64, 32), ('conv', 3, 3, 128, 80))
+
+    def __call__(self, inputs):
+        flow, corr = inputs
+        cor = self._conv(corr, 'convc1', 'relu')
+        flo = self._conv(self._conv(flow, 'convf1', 'relu'), 'convf2', 'relu')
+        out = self._conv(torch.cat([cor, flo], dim=-1), 'conv', 'relu')
+        return torch.cat([out, _lib.f32c(flow)], dim=-1)
+
+
+class BasicMotionEncoder(_ConvLayers):
+    """Reference update.py:88-106 -> concat([conv(...), flow]) with 128 channels."""
+    _spec = (('convc1', 1, 1, 324, 256), ('convc2', 3, 3, 256, 192), ('convf1', 7, 7, 2, 128),
+             ('convf2', 3, 3, 128, 64), ('conv', 3, 3, 256, 126))
+
+    def __call__(self, inputs):
+        flow, corr = inputs
+        cor = self._conv(self._conv(corr, 'convc1', 'relu'), 'convc2', 'relu')
+        flo = self._conv(self._conv(flow, 'convf1', 'relu'), 'convf2', 'relu')
+        out = self._conv(torch.cat([cor, flo], dim=-1), 'conv', 'relu')
+        return torch.cat([out, _lib.f32c(flow)], dim=-1)

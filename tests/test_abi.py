@@ -93,3 +93,32 @@ def test_losses_match_reference_known_answers():
     info = end_point_error([flow_gt, valid], preds[-1])
     np.testing.assert_almost_equal(float(info['epe']), np.mean(np.arange(1, 9) - 0.1), decimal=2)
     np.testing.assert_almost_equal(float(info['u3']), 3 / 8, decimal=2)
+
+
+def test_workspace_and_shape_errors_are_detected_on_the_host(L):
+    """Every entry point validates sizes before it launches anything: too-small workspaces / prepared buffers and
+    inconsistent shapes come back as raft_status codes even without a GPU (pointers are never dereferenced here)."""
+    fake = ctypes.c_void_p(0x1000)
+    ptrs4 = (ctypes.c_void_p * 4)(0x1000, 0x2000, 0x3000, 0x4000)
+    # correlation: F16X2 needs scratch
+    assert L.raft_b200_corr_pyramid_build(fake, fake, 1, 8, 8, 64, 4, ptrs4, fake, 16, 1, None) == -3
+    assert L.raft_b200_corr_pyramid_build(fake, fake, 1, 8, 8, 64, 4, ptrs4, None, 0, 1, None) == -3
+    assert L.raft_b200_corr_pyramid_build(fake, fake, 1, 4, 8, 64, 4, ptrs4, fake, 1 << 30, 1, None) == -2   # level 3 empty
+    assert L.raft_b200_corr_pyramid_build(None, fake, 1, 8, 8, 64, 4, ptrs4, fake, 1 << 30, 1, None) == -1
+    # lookup: output row must hold levels*(2r+1)^2 channels
+    assert L.raft_b200_corr_lookup(ptrs4, fake, 1, 8, 8, 4, 4, fake, 100, None) == -2
+    # update block: workspace too small
+    assert L.raft_b200_update_basic(fake, fake, fake, fake, fake, fake, fake, fake, 1, 8, 8, fake, 1024, 1, None) == -3
+    assert L.raft_b200_update_small(fake, fake, fake, fake, fake, fake, fake, 1, 8, 8, fake, 1024, 0, None) == -3
+    assert L.raft_b200_update_basic(fake, fake, fake, fake, fake, fake, None, fake, 1, 8, 8, fake, 1 << 40, 7, None) == -1   # bad precision
+    # loop: radius / levels must match the variant's correlation channel count
+    pyr = (ctypes.c_void_p * 4)(0x1000, 0x2000, 0x3000, 0x4000)
+    ups = (ctypes.c_void_p * 2)(0x1000, 0x2000)
+    assert L.raft_b200_forward_loop(0, fake, pyr, 4, 3, fake, fake, fake, ups, 2, 1, 8, 8, fake, 1 << 40, 1, None) == -2
+    assert L.raft_b200_forward_loop(0, fake, pyr, 4, 4, fake, fake, fake, ups, 2, 1, 8, 8, fake, 64, 1, None) == -3
+    # encoder
+    nbytes = ctypes.c_size_t()
+    assert L.raft_b200_encoder_prepared_bytes(0, 250, ctypes.byref(nbytes)) == -2        # out_dim must be a multiple of 32
+    assert L.raft_b200_encoder_workspace_bytes(0, 4, 448, 512, ctypes.byref(nbytes)) == 0 and nbytes.value > (1 << 28)
+    assert L.raft_b200_encoder_forward(0, 1, 256, fake, fake, 1, 64, 64, 0, 1, fake, fake, 1024, None) == -3
+    assert L.raft_b200_conv2d(fake, fake, fake, 1, 8, 8, 4, 2, 3, 8, 0, fake, 8, 0, None) == -2      # even kernel size

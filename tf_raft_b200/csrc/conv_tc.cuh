@@ -250,6 +250,145 @@ __device__ __noinline__ void tc_epilogue_chunk(const TcConvParams& pp, float* v,
     }
   }
 }
+// ------------------------------------------------------------------------------------------------
+// Register-resident epilogue of one 32-column chunk of one pixel row (thread == row).
+//
+// Measured: with 227 KB of the unified L1/shared array configured as shared memory, per-thread LOCAL memory does not
+// stay in L1, so the earlier out-of-line routine (accumulators staged through a local buffer, rolled loops) paid an
+// L2 round trip per access: ~32-37 k cycles per tile regardless of the tile width.  Here nothing leaves registers:
+// the routine is inlined and specialised on the epilogue mode at compile time, loops are fully unrolled so the
+// independent 16-byte global loads (bias, h, z, residual) are all in flight together, and the activation math uses
+// the fast exp / reciprocal units (|error| ~1e-7, far inside the parity budget).
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__device__ __forceinline__ void tc_epilogue_regs(const TcConvParams& p, float (&v)[32], size_t pix, int col, int ncol,
+                                                 float inv_scale) {
+  // bias + folded BatchNorm affine (arrays are zero-padded past the last column)
+  if (p.bias) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 bq = ldg4(p.bias + col + 4 * q);
+      v[4 * q] = v[4 * q] * inv_scale + bq.x; v[4 * q + 1] = v[4 * q + 1] * inv_scale + bq.y;
+      v[4 * q + 2] = v[4 * q + 2] * inv_scale + bq.z; v[4 * q + 3] = v[4 * q + 3] * inv_scale + bq.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= inv_scale;
+  }
+  if (MODE == EPI_LINEAR && p.post_scale) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 sc = ldg4(p.post_scale + col + 4 * q), sh = ldg4(p.post_shift + col + 4 * q);
+      v[4 * q] = v[4 * q] * sc.x + sh.x; v[4 * q + 1] = v[4 * q + 1] * sc.y + sh.y;
+      v[4 * q + 2] = v[4 * q + 2] * sc.z + sh.z; v[4 * q + 3] = v[4 * q + 3] * sc.w + sh.w;
+    }
+  }
+
+  __half* dhi = nullptr;
+  __half* dlo = nullptr;
+  if (MODE == EPI_LINEAR) {
+    const bool full = col + 32 <= p.n_total;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (p.act == ACT_RELU) v[j] = fmaxf(v[j], 0.0f);
+      v[j] *= p.out_scale;
+    }
+    if (full) {
+      if (p.residual) {
+        const float* rp = p.residual + pix * (size_t)p.res_stride + p.res_c0 + col;
+        if (((p.res_stride | p.res_c0) & 3) == 0) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 r4 = ldg4(rp + 4 * q);
+            v[4 * q] = fmaxf(v[4 * q] + r4.x, 0.f); v[4 * q + 1] = fmaxf(v[4 * q + 1] + r4.y, 0.f);
+            v[4 * q + 2] = fmaxf(v[4 * q + 2] + r4.z, 0.f); v[4 * q + 3] = fmaxf(v[4 * q + 3] + r4.w, 0.f);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + __ldg(rp + j), 0.f);
+        }
+      }
+    } else {                                           // ragged tail: concat columns / zeros / residual per column
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int cj = col + j - p.n_total;
+        if (cj >= 0) v[j] = (p.concat_src && cj < p.concat_n) ? __ldg(p.concat_src + pix * p.concat_n + cj) : 0.0f;
+        else if (p.residual) v[j] = fmaxf(v[j] + __ldg(p.residual + pix * (size_t)p.res_stride + p.res_c0 + col + j), 0.0f);
+      }
+    }
+    if (p.out_f32) {
+      const int nvalid = min(ncol, p.n_total - col);
+      float* dst = p.out_f32 + pix * (size_t)p.f32_stride + p.f32_c0 + col;
+      if (nvalid == 32 && ((p.f32_stride | p.f32_c0) & 3) == 0) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) st4(dst + 4 * q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < nvalid) dst[j] = v[j];
+      }
+    }
+    if (p.out_hi && ncol == 32) {
+      const size_t o = pix * (size_t)p.h_stride + p.h_c0 + col;
+      dhi = p.out_hi + o;
+      dlo = p.out_lo + o;
+    }
+  } else if (MODE == EPI_GRU_ZR) {
+    if (col < p.hid) {                                 // z gate -> fp32 plane
+      float* dst = p.z + pix * (size_t)p.hid + col;
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        st4(dst + 4 * q, make_float4(fast_sigmoid(v[4 * q]), fast_sigmoid(v[4 * q + 1]), fast_sigmoid(v[4 * q + 2]),
+                                     fast_sigmoid(v[4 * q + 3])));
+    } else {                                           // r gate -> r*h, re-split for the q convolution
+      const int hc = col - p.hid;
+      const float* hp = p.h + pix * (size_t)p.hid + hc;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 hv = ldg4(hp + 4 * q);
+        v[4 * q] = fast_sigmoid(v[4 * q]) * hv.x; v[4 * q + 1] = fast_sigmoid(v[4 * q + 1]) * hv.y;
+        v[4 * q + 2] = fast_sigmoid(v[4 * q + 2]) * hv.z; v[4 * q + 3] = fast_sigmoid(v[4 * q + 3]) * hv.w;
+      }
+      const size_t o = pix * (size_t)p.h_stride + p.h_c0 + hc;
+      dhi = p.out_hi + o;
+      dlo = p.out_lo + o;
+    }
+  } else if (MODE == EPI_GRU_Q) {                      // h = (1-z)*h + z*tanh(v), in place
+    float* hrow = p.h + pix * (size_t)p.hid + col;
+    const float* zp = p.z + pix * (size_t)p.hid + col;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 zv = ldg4(zp + 4 * q), hv = ld4(hrow + 4 * q);
+      v[4 * q] = (1.0f - zv.x) * hv.x + zv.x * fast_tanh(v[4 * q]);
+      v[4 * q + 1] = (1.0f - zv.y) * hv.y + zv.y * fast_tanh(v[4 * q + 1]);
+      v[4 * q + 2] = (1.0f - zv.z) * hv.z + zv.z * fast_tanh(v[4 * q + 2]);
+      v[4 * q + 3] = (1.0f - zv.w) * hv.w + zv.w * fast_tanh(v[4 * q + 3]);
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) st4(hrow + 4 * q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+    const size_t o = pix * (size_t)p.h_stride + p.h_c0 + col;
+    dhi = p.out_hi + o;
+    dlo = p.out_lo + o;
+  }
+
+  if (dhi) {                                           // fp16 hi/lo re-split, 8 channels (16 bytes) per store
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t ph[4], pl[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        __half h0, l0, h1, l1;
+        split_f16(v[8 * q + 2 * e], h0, l0);
+        split_f16(v[8 * q + 2 * e + 1], h1, l1);
+        ph[e] = pack_h2(h0, h1);
+        pl[e] = pack_h2(l0, l1);
+      }
+      reinterpret_cast<uint4*>(dhi)[q] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+      reinterpret_cast<uint4*>(dlo)[q] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+    }
+  }
+}
+
 // Coalesced store of one 32x32 accumulator block of the correlation volume (patch = swizzled transposition buffer):
 // 8 lanes x 16 bytes cover a row, so a warp writes 4 full 128-byte pyramid rows per instruction.
 __device__ __noinline__ void tc_store_corr_block(const float* patch, long long pix_lane, float* out, int stride, int col0,
@@ -492,14 +631,14 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_tc_kernel(const _
           }
         } else if (x < p.W && y < p.H) {   // (convolution instantiation)
           const size_t pix = ((size_t)b * p.H + y) * p.W + x;
-          __align__(16) float buf32[32];
 #pragma unroll
           for (int ci = 0; ci < kMaxCh; ++ci) {
             if (ci < my_chunks) {
               const int c0 = (chunk0 + ci) * 32;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) buf32[j] = racc[ci][j];
-              tc_epilogue_chunk(p, buf32, pix, nt * p.bn + c0, min(32, p.bn - c0), inv_scale);
+              const int ncol = min(32, p.bn - c0);
+              if (p.mode == EPI_LINEAR) tc_epilogue_regs<EPI_LINEAR>(p, racc[ci], pix, nt * p.bn + c0, ncol, inv_scale);
+              else if (p.mode == EPI_GRU_ZR) tc_epilogue_regs<EPI_GRU_ZR>(p, racc[ci], pix, nt * p.bn + c0, ncol, inv_scale);
+              else tc_epilogue_regs<EPI_GRU_Q>(p, racc[ci], pix, nt * p.bn + c0, ncol, inv_scale);
             }
           }
         }
@@ -548,6 +687,17 @@ inline int tc_finalize(TcConvParams& p) {
   return nst * p.stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + patch;
 }
 
+// Promotion/epilogue warps of the convolution instantiation: kEpiWarpsConv by default, RAFT_B200_EPI_WARPS=8|16 overrides.
+inline int tc_epi_warps() {
+  static int w = -1;
+  if (w < 0) {
+    const char* e = getenv("RAFT_B200_EPI_WARPS");
+    const int v = e ? atoi(e) : kEpiWarpsConv;
+    w = (v == 8) ? 8 : 16;
+  }
+  return w;
+}
+
 // Preferred cluster size (1, 2 or 4); RAFT_B200_CLUSTER overrides the default of 2.
 inline int tc_cluster_pref() {
   static int pref = -1;
@@ -576,7 +726,8 @@ inline int tc_launch(TcConvParams& p, int n_tiles_n, cudaStream_t stream) {
   if (p.nstages < 2) return RAFT_ERR_UNSUPPORTED;
   static bool attr_set = false;   // benign race: idempotent
   if (!attr_set) {
-    RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<false, kEpiWarpsConv>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<true, kEpiWarpsCorr>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
@@ -586,7 +737,8 @@ inline int tc_launch(TcConvParams& p, int n_tiles_n, cudaStream_t stream) {
   const long ntiles = (long)mtiles * n_tiles_n;
   const unsigned grid = (unsigned)(ntiles < kNumSMs ? ntiles : kNumSMs);   // one persistent CTA per SM
   if (p.mode == EPI_CORR) conv_tc_kernel<true, kEpiWarpsCorr><<<grid, 64 + 32 * kEpiWarpsCorr, smem, stream>>>(p);
-  else conv_tc_kernel<false, kEpiWarpsConv><<<grid, 64 + 32 * kEpiWarpsConv, smem, stream>>>(p);
+  else if (tc_epi_warps() == 8) conv_tc_kernel<false, 8><<<grid, 64 + 32 * 8, smem, stream>>>(p);
+  else conv_tc_kernel<false, 16><<<grid, 64 + 32 * 16, smem, stream>>>(p);
   return raft_launch_status();
 }
 

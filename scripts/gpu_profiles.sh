@@ -4,20 +4,27 @@ set -u
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
+if [ -z "${SKIP_TESTS:-}" ]; then
 timeout 900 python -m pytest tests -m gpu -q -s -p no:cacheprovider > gpurun_out/t_all.log 2>&1; echo "pytest exit $? : $(tail -n 1 gpurun_out/t_all.log)"
 grep -hE "first sampler|FAILED|Error" gpurun_out/t_all.log | head -10
+fi
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?: $(tail -n 2 gpurun_out/smoke.log | tr '\n' ' ')"
 nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap --format=csv -lms 200 > gpurun_out/clocks.csv &
 SMI=$!
 timeout 300 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_r01.json 2> gpurun_out/bench_r01.err; echo "bench exit $?"
 kill $SMI
+if [ -z "${FAST:-}" ]; then
 timeout 300 python bench.py --steps 10 --warmup 3 --precision fp32 > gpurun_out/bench_r01_fp32.json 2> gpurun_out/bench_r01_fp32.err; echo "bench fp32 exit $?"
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_r01_reference.json 2> /dev/null; echo "bench ref exit $?"
+fi
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_r01.csv python bench.py --steps 2 --warmup 3 --no-graph > gpurun_out/ncu_bench.log 2>&1; echo "ncu launches exit $?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 232 -c 3 -o gpurun_out/prof_r01_conv_tc python scripts/profile_loop.py f16x2 2 > gpurun_out/ncu_full.log 2>&1; echo "ncu full exit $?"
 timeout 300 ncu --set full --clock-control none -k regex:corr_lookup_kernel -s 14 -c 1 -o gpurun_out/prof_r01_lookup python scripts/profile_loop.py f16x2 2 > gpurun_out/ncu_full2.log 2>&1; echo "ncu lookup exit $?"
 python tools/timeline.py 4 > gpurun_out/timeline_zr1.log 2>&1
-./tools/tma_probe > gpurun_out/tma_probe.log 2>&1
+[ -z "${FAST:-}" ] && ./tools/tma_probe > gpurun_out/tma_probe.log 2>&1
+for l in 0 5 8; do python tools/timeline.py $l 2>&1 | tail -n 1 >> gpurun_out/timeline_zr1.log; done
+python tools/timeline_enc.py 1 > gpurun_out/timeline_enc1.log 2>&1
+RAFT_B200_ENC_GROUP=2 timeout 200 python bench.py --steps 10 --warmup 3 --quick > gpurun_out/bench_r01_encgroup2.json 2> /dev/null; echo "bench encgroup2 exit $?"
 python - <<'PY'
 import json
 for f in ('bench_r01', 'bench_r01_fp32', 'bench_r01_reference'):

@@ -7,6 +7,7 @@ namespace raft {
 thread_local long long g_launches = 0;
 int g_dbg_layer = -1;
 long long* g_dbg_buf = nullptr;
+int g_dbg_count = 0;               // encoder convolutions launched since the timeline was armed (tc_layer >= 1000)
 
 static int check_dims(int B, int h, int w) { return (B > 0 && h > 0 && w > 0) ? 0 : RAFT_ERR_BAD_SHAPE; }
 
@@ -427,6 +428,7 @@ int raft_b200_device_ok(int device) {
 long long raft_b200_launch_count(void) { return g_launches; }
 void raft_b200_debug_timeline(int tc_layer, long long* device_buf_2048) {
   g_dbg_layer = tc_layer;
+  g_dbg_count = 0;
   g_dbg_buf = device_buf_2048;
 }
 void raft_b200_launch_count_reset(void) { g_launches = 0; }

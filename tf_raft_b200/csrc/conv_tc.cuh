@@ -72,6 +72,8 @@ struct alignas(64) TcConvParams {
   const float* concat_src; int concat_n;   // EPI_LINEAR: fp32 (px, concat_n) appended at columns [n_total, n_total+concat_n)
   float* z; int hid;                       // GRU: z plane (px, hid) fp32
   float* h;                                // GRU: hidden state (px, hid) fp32, updated in place by EPI_GRU_Q
+  int b_stationary;      // 1: all weights of the layer stay resident in shared memory (loaded once per CTA)
+  int b_region_bytes;    // bytes of that resident region (0 otherwise)
   long long* dbg;                          // optional timeline of CTA 0 (tools/timeline.py): [4][512] clock64 stamps
 };
 
@@ -389,6 +391,148 @@ __device__ __forceinline__ void tc_epilogue_regs(const TcConvParams& p, float (&
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Coalesced epilogue of a 32-row x 16-column accumulator block, AFTER transposition through shared memory:
+// lane l holds rows (l>>2) + 8k (k = 0..3) and columns col .. col+3 of the block, so every global access of a warp
+// touches 8 rows x 64 contiguous bytes instead of 32 rows x 16 bytes.  Measured on the thread-per-row form: the LSU
+// retires about one distinct 128-byte line per cycle, which made the epilogue of a 256-column tile cost 14-22 k cycles.
+// pixr[k] is the flat pixel index of row k (-1 = outside the image).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_split4(__half* hi, __half* lo, size_t o, bool aligned, const float (&v)[4]) {
+  __half h[4], l[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) split_f16(v[e], h[e], l[e]);
+  if (aligned) {
+    *reinterpret_cast<uint2*>(hi + o) = make_uint2(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]));
+    *reinterpret_cast<uint2*>(lo + o) = make_uint2(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]));
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      hi[o + e] = h[e];
+      lo[o + e] = l[e];
+    }
+  }
+}
+
+template <int MODE>
+__device__ __forceinline__ void tc_epilogue_t(const TcConvParams& p, float (&v)[4][4], const int (&pixr)[4], int col,
+                                              float inv_scale) {
+  if (p.bias) {
+    const float4 bq = ldg4(p.bias + col);            // bias / affine arrays are zero-padded past the last column
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      v[k][0] = v[k][0] * inv_scale + bq.x; v[k][1] = v[k][1] * inv_scale + bq.y;
+      v[k][2] = v[k][2] * inv_scale + bq.z; v[k][3] = v[k][3] * inv_scale + bq.w;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[k][e] *= inv_scale;
+  }
+
+  if (MODE == EPI_LINEAR) {
+    if (p.post_scale) {                                // folded BatchNorm / InstanceNorm affine
+      const float4 sc = ldg4(p.post_scale + col), sh = ldg4(p.post_shift + col);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        v[k][0] = v[k][0] * sc.x + sh.x; v[k][1] = v[k][1] * sc.y + sh.y;
+        v[k][2] = v[k][2] * sc.z + sh.z; v[k][3] = v[k][3] * sc.w + sh.w;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (p.act == ACT_RELU) v[k][e] = fmaxf(v[k][e], 0.0f);
+        v[k][e] *= p.out_scale;
+      }
+    const int nvalid = p.n_total - col;                // real output columns among my 4
+    const bool res_vec = ((p.res_stride | p.res_c0) & 3) == 0;
+    const bool f32_vec = ((p.f32_stride | p.f32_c0) & 3) == 0;
+    const bool h_vec = ((p.h_stride | p.h_c0) & 3) == 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (pixr[k] < 0) continue;
+      const size_t pix = (size_t)pixr[k];
+      if (nvalid >= 4) {
+        if (p.residual) {
+          const float* rp = p.residual + pix * (size_t)p.res_stride + p.res_c0 + col;
+          if (res_vec) {
+            const float4 r4 = ldg4(rp);
+            v[k][0] = fmaxf(v[k][0] + r4.x, 0.f); v[k][1] = fmaxf(v[k][1] + r4.y, 0.f);
+            v[k][2] = fmaxf(v[k][2] + r4.z, 0.f); v[k][3] = fmaxf(v[k][3] + r4.w, 0.f);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[k][e] = fmaxf(v[k][e] + __ldg(rp + e), 0.f);
+          }
+        }
+      } else {                                         // ragged tail: concatenated columns / zero padding
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int cj = e - nvalid;
+          if (cj >= 0) v[k][e] = (p.concat_src && cj < p.concat_n) ? __ldg(p.concat_src + pix * p.concat_n + cj) : 0.0f;
+          else if (p.residual) v[k][e] = fmaxf(v[k][e] + __ldg(p.residual + pix * (size_t)p.res_stride + p.res_c0 + col + e), 0.0f);
+        }
+      }
+      if (p.out_f32 && nvalid > 0) {
+        float* dst = p.out_f32 + pix * (size_t)p.f32_stride + p.f32_c0 + col;
+        if (nvalid >= 4 && f32_vec) st4(dst, make_float4(v[k][0], v[k][1], v[k][2], v[k][3]));
+        else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (e < nvalid) dst[e] = v[k][e];
+        }
+      }
+      if (p.out_hi) store_split4(p.out_hi, p.out_lo, pix * (size_t)p.h_stride + p.h_c0 + col, h_vec, v[k]);
+    }
+  } else if (MODE == EPI_GRU_ZR) {
+    const bool h_vec = ((p.h_stride | p.h_c0) & 3) == 0;
+    if (col < p.hid) {                                 // z gate -> fp32 plane
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (pixr[k] >= 0)
+          st4(p.z + (size_t)pixr[k] * p.hid + col,
+              make_float4(fast_sigmoid(v[k][0]), fast_sigmoid(v[k][1]), fast_sigmoid(v[k][2]), fast_sigmoid(v[k][3])));
+    } else {                                           // r gate -> r*h, re-split for the q convolution
+      const int hc = col - p.hid;
+      float4 hv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) hv[k] = pixr[k] >= 0 ? ldg4(p.h + (size_t)pixr[k] * p.hid + hc) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (pixr[k] < 0) continue;
+        v[k][0] = fast_sigmoid(v[k][0]) * hv[k].x; v[k][1] = fast_sigmoid(v[k][1]) * hv[k].y;
+        v[k][2] = fast_sigmoid(v[k][2]) * hv[k].z; v[k][3] = fast_sigmoid(v[k][3]) * hv[k].w;
+        store_split4(p.out_hi, p.out_lo, (size_t)pixr[k] * p.h_stride + p.h_c0 + hc, h_vec, v[k]);
+      }
+    }
+  } else if (MODE == EPI_GRU_Q) {                      // h = (1-z)*h + z*tanh(v), in place
+    const bool h_vec = ((p.h_stride | p.h_c0) & 3) == 0;
+#pragma unroll
+    for (int k0 = 0; k0 < 4; k0 += 2) {                // two rows at a time: loads in flight together, registers bounded
+      float4 zv[2], hv[2];
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        const bool ok = pixr[k0 + kk] >= 0;
+        zv[kk] = ok ? ldg4(p.z + (size_t)pixr[k0 + kk] * p.hid + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+        hv[kk] = ok ? ld4(p.h + (size_t)pixr[k0 + kk] * p.hid + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        const int k = k0 + kk;
+        if (pixr[k] < 0) continue;
+        v[k][0] = (1.0f - zv[kk].x) * hv[kk].x + zv[kk].x * fast_tanh(v[k][0]);
+        v[k][1] = (1.0f - zv[kk].y) * hv[kk].y + zv[kk].y * fast_tanh(v[k][1]);
+        v[k][2] = (1.0f - zv[kk].z) * hv[kk].z + zv[kk].z * fast_tanh(v[k][2]);
+        v[k][3] = (1.0f - zv[kk].w) * hv[kk].w + zv[kk].w * fast_tanh(v[k][3]);
+        st4(p.h + (size_t)pixr[k] * p.hid + col, make_float4(v[k][0], v[k][1], v[k][2], v[k][3]));
+        store_split4(p.out_hi, p.out_lo, (size_t)pixr[k] * p.h_stride + p.h_c0 + col, h_vec, v[k]);
+      }
+    }
+  }
+}
+
 // Coalesced store of one 32x32 accumulator block of the correlation volume (patch = swizzled transposition buffer):
 // 8 lanes x 16 bytes cover a row, so a warp writes 4 full 128-byte pyramid rows per instruction.
 __device__ __noinline__ void tc_store_corr_block(const float* patch, long long pix_lane, float* out, int stride, int col0,
@@ -424,7 +568,7 @@ __device__ __noinline__ void tc_store_corr_block(const float* patch, long long p
 
 // kCorr selects the correlation epilogue at compile time so that its transposition path costs the convolution
 // instantiation neither registers nor code.
-template <bool kCorr, int kEpiWarps>
+template <bool kCorr, int kEpiWarps, bool kRowEpi>
 __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_tc_kernel(const __grid_constant__ TcConvParams p) {
 #if defined(__CUDA_ARCH__)
   // Persistent: CTA c processes output tiles c, c + gridDim.x, ...  A tile is (pixel tile, column tile).  All
@@ -434,12 +578,15 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_tc_kernel(const _
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nst = p.nstages;
   const int b_bytes = p.bn * kChunkK * 2;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)nst * p.stage_bytes);
+  uint8_t* bsm = smem;                                        // resident weights (b_stationary), else empty
+  uint8_t* stages = smem + p.b_region_bytes;                  // ring of nst stages
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stages + (size_t)nst * p.stage_bytes);
   uint64_t* empty_bar = full_bar + nst;
   uint64_t* acc_full = empty_bar + nst;      // [2] issuer -> promotion warps
   uint64_t* acc_empty = acc_full + 2;        // [2] promotion warps -> issuer
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  float* patches = reinterpret_cast<float*>(smem + (size_t)nst * p.stage_bytes + 256);   // EPI_CORR only: 8 x 4 KB
+  uint64_t* b_full = acc_empty + 2;          // resident weights landed
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(b_full + 1);
+  float* patches = reinterpret_cast<float*>(stages + (size_t)nst * p.stage_bytes + 256);   // transposition patches (if any)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -465,6 +612,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_tc_kernel(const _
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], 4 * ((nchunks32 + chunks_per_part - 1) / chunks_per_part));   // one arrival per participating warp
     }
+    mbar_init(b_full, 1);
     fence_mbar_init();
     prefetch_tmap(&p.a_map[0]);
     prefetch_tmap(&p.b_map);
@@ -483,6 +631,15 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_tc_kernel(const _
     // ===================== TMA producer =====================
     if (elect_one()) {
       int it = 0;
+      if (p.b_stationary) {
+        // Measured (tools/tma_probe.cu, timelines): a TMA box costs max(~616 cycles, bytes / 53 B/clk) and boxes are
+        // served one after the other, so for narrow layers (cout 64: a 16 KB weight box per chunk) the weight box
+        // costs as much as the 32 KB activation box.  When all taps of the layer fit, fetch them ONCE per CTA --
+        // one box per 64-channel slice, [plane][tap][cout][64] -- and stream only activations afterwards.
+        mbar_arrive_expect_tx(b_full, (uint32_t)p.b_region_bytes);
+        for (int kc = 0; kc < chunks_per_tap; ++kc)
+          tma_load_4d(bsm + (size_t)kc * 2 * ntaps * b_bytes, &p.b_map, b_full, kc * kChunkK, 0, 0, 0);
+      }
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int nt = t / mtiles;
         int mt = t - nt * mtiles;
@@ -501,12 +658,12 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_tc_kernel(const _
               const uint32_t phase = (uint32_t)(it / nst) & 1u;
               mbar_wait(&empty_bar[s], phase ^ 1u);
               if (p.dbg && blockIdx.x == 0 && it < 512) p.dbg[it] = clock64();              // slot free
-              uint8_t* st = smem + (size_t)s * p.stage_bytes;
+              uint8_t* st = stages + (size_t)s * p.stage_bytes;
               mbar_arrive_expect_tx(&full_bar[s], (uint32_t)p.stage_bytes);
               const int c = p.seg_c0[seg] + ch * kChunkK;
               // two boxes per stage: [A_hi | A_lo] and [B_hi | B_lo] (TMA cost is per box, not per byte)
               tma_load_5d(st, &p.a_map[seg], &full_bar[s], c, x0 + dx, y0 + dy, b, 0);
-              tma_load_4d(st + 2 * kABytes, &p.b_map, &full_bar[s], kc * kChunkK, n0, tcoord, 0);
+              if (!p.b_stationary) tma_load_4d(st + 2 * kABytes, &p.b_map, &full_bar[s], kc * kChunkK, n0, tcoord, 0);
             }
           }
         }
@@ -516,12 +673,17 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_tc_kernel(const _
     // ===================== MMA issuer =====================
     const uint32_t idesc = make_idesc_f16(kTileM, p.bn);
     int it = 0, gg = 0;
+    if (p.b_stationary) {
+      mbar_wait(b_full, 0u);
+      tc_fence_after();
+    }
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
       int done = 0;
       for (int g = 0; g < ngroups; ++g, ++gg) {
         const int buf = gg & 1;
         mbar_wait(&acc_empty[buf], ((uint32_t)(gg >> 1) & 1u) ^ 1u);   // promotion warps drained this buffer
         tc_fence_after();
+        if (p.dbg && blockIdx.x == 0 && gg < 256 && lane == 0) p.dbg[1024 + 256 + gg] = clock64();   // issuer owns the buffer
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.bn);
         const int gend = min(total, done + gsz);
         for (int first = 1; done < gend; ++done, ++it, first = 0) {
@@ -531,11 +693,17 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_tc_kernel(const _
           tc_fence_after();
           if (p.dbg && blockIdx.x == 0 && it < 512 && lane == 0) p.dbg[512 + it] = clock64();   // data landed
           if (elect_one()) {
-            const uint32_t sa = smem_u32(smem + (size_t)s * p.stage_bytes);
+            const uint32_t sa = smem_u32(stages + (size_t)s * p.stage_bytes);
+            uint32_t sb_hi = sa + 2 * kABytes, sb_lo = sa + 2 * kABytes + b_bytes;
+            if (p.b_stationary) {                            // chunk `done` of the tile = (tap, 64-channel slice kc)
+              const int tap = done / chunks_per_tap, kc = done - tap * chunks_per_tap;
+              sb_hi = smem_u32(bsm) + (uint32_t)((kc * 2 * ntaps + tap) * b_bytes);
+              sb_lo = sb_hi + (uint32_t)(ntaps * b_bytes);
+            }
             const uint64_t a_hi = make_desc_sw128(sa);
             const uint64_t a_lo = make_desc_sw128(sa + kABytes);
-            const uint64_t b_hi = make_desc_sw128(sa + 2 * kABytes);
-            const uint64_t b_lo = make_desc_sw128(sa + 2 * kABytes + b_bytes);
+            const uint64_t b_hi = make_desc_sw128(sb_hi);
+            const uint64_t b_lo = make_desc_sw128(sb_lo);
 #pragma unroll
             for (int k = 0; k < kChunkK / 16; ++k)   // +32 bytes per K=16 step == +2 in 16-byte units
               umma_f16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (!first || k > 0) ? 1u : 0u);
@@ -574,7 +742,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_tc_kernel(const _
           const int buf = gg & 1;
           mbar_wait(&acc_full[buf], (uint32_t)(gg >> 1) & 1u);
           tc_fence_after();
-          if (p.dbg && blockIdx.x == 0 && gg < 512 && warp == 2 && lane == 0) p.dbg[1024 + gg] = clock64();   // group retired
+          if (p.dbg && blockIdx.x == 0 && gg < 256 && warp == 2 && lane == 0) p.dbg[1024 + gg] = clock64();   // group retired
 #pragma unroll
           for (int ci = 0; ci < kMaxCh; ++ci) {
             if (ci < my_chunks) {
@@ -597,7 +765,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_tc_kernel(const _
           }
           tc_fence_before();
           __syncwarp();
-          if (p.dbg && blockIdx.x == 0 && gg < 512 && warp == 2 && lane == 0) p.dbg[1536 + gg] = clock64();   // group drained
+          if (p.dbg && blockIdx.x == 0 && gg < 256 && warp == 2 && lane == 0) p.dbg[1536 + gg] = clock64();   // group drained
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
 
@@ -629,20 +797,59 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_tc_kernel(const _
                                   p.corr_div);
             }
           }
-        } else if (x < p.W && y < p.H) {   // (convolution instantiation)
-          const size_t pix = ((size_t)b * p.H + y) * p.W + x;
+        } else if constexpr (kRowEpi) {    // convolution, thread-per-row register epilogue (EPI_LINEAR, EPI_GRU_ZR)
+          if (x < p.W && y < p.H) {
+            const size_t pix = ((size_t)b * p.H + y) * p.W + x;
+#pragma unroll
+            for (int ci = 0; ci < kMaxCh; ++ci) {
+              if (ci < my_chunks) {
+                const int c0 = (chunk0 + ci) * 32;
+                const int ncol = min(32, p.bn - c0);
+                if (p.mode == EPI_LINEAR) tc_epilogue_regs<EPI_LINEAR>(p, racc[ci], pix, nt * p.bn + c0, ncol, inv_scale);
+                else tc_epilogue_regs<EPI_GRU_ZR>(p, racc[ci], pix, nt * p.bn + c0, ncol, inv_scale);
+              }
+            }
+          }
+        } else {                           // EPI_GRU_Q: coalesced epilogue through a 32 x 16 transposition patch (measured:
+                                           // 13 k cycles vs 23 k thread-per-row; the other modes measured slower transposed)
+          float4* patch4 = reinterpret_cast<float4*>(patches + (warp - 2) * 512);
+          const int pix_own = (x < p.W && y < p.H) ? (int)(((size_t)b * p.H + y) * p.W + x) : -1;
+          int pixr[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) pixr[k] = __shfl_sync(0xffffffffu, pix_own, (lane >> 2) + 8 * k);
+          const int c4 = lane & 3;
+          const int wsw = (lane >> 1) & 3, rsw = (lane >> 3) & 3;   // XOR swizzles: conflict-free 16-byte writes and reads
 #pragma unroll
           for (int ci = 0; ci < kMaxCh; ++ci) {
             if (ci < my_chunks) {
-              const int c0 = (chunk0 + ci) * 32;
-              const int ncol = min(32, p.bn - c0);
-              if (p.mode == EPI_LINEAR) tc_epilogue_regs<EPI_LINEAR>(p, racc[ci], pix, nt * p.bn + c0, ncol, inv_scale);
-              else if (p.mode == EPI_GRU_ZR) tc_epilogue_regs<EPI_GRU_ZR>(p, racc[ci], pix, nt * p.bn + c0, ncol, inv_scale);
-              else tc_epilogue_regs<EPI_GRU_Q>(p, racc[ci], pix, nt * p.bn + c0, ncol, inv_scale);
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                const int c0 = (chunk0 + ci) * 32 + hh * 16;
+                if (c0 < p.bn) {
+                  __syncwarp();
+#pragma unroll
+                  for (int q = 0; q < 4; ++q)
+                    patch4[lane * 4 + (q ^ wsw)] = make_float4(racc[ci][hh * 16 + 4 * q], racc[ci][hh * 16 + 4 * q + 1],
+                                                               racc[ci][hh * 16 + 4 * q + 2], racc[ci][hh * 16 + 4 * q + 3]);
+                  __syncwarp();
+                  float v[4][4];
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const float4 t4 = patch4[((lane >> 2) + 8 * k) * 4 + (c4 ^ rsw)];
+                    v[k][0] = t4.x; v[k][1] = t4.y; v[k][2] = t4.z; v[k][3] = t4.w;
+                  }
+                  const int col = nt * p.bn + c0 + 4 * c4;
+                  tc_epilogue_t<EPI_GRU_Q>(p, v, pixr, col, inv_scale);
+                }
+              }
             }
           }
         }
-        if (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0) p.dbg[2047] = clock64();   // epilogue of the tile done
+        if (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0) {
+          p.dbg[2047] = clock64();                                           // epilogue of the (last) tile done
+          const int tl = (t - (int)blockIdx.x) / (int)gridDim.x;
+          if (tl < 255) p.dbg[1536 + 256 + tl] = clock64();                   // ... of every tile
+        }
       }
     }
   }
@@ -656,6 +863,8 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_tc_kernel(const _
 // ------------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------------
+inline bool tc_uses_patch(int mode) { return mode == EPI_CORR || mode == EPI_GRU_Q; }
+
 inline void tc_pick_tile(int W, int H, int* tw, int* th) {
   // TW*TH = 128 with TW a power of two; minimise padded area, prefer wide tiles on ties.
   long best = -1;
@@ -676,26 +885,43 @@ inline int tc_finalize(TcConvParams& p) {
   p.tiles_x = ceil_div(p.W, p.TW);
   p.tiles_y = ceil_div(p.H, p.TH);
   p.stage_bytes = 2 * kABytes + 2 * p.bn * kChunkK * 2;
-  const int patch = p.mode == EPI_CORR ? kEpiPatchBytes : 0;
-  int nst = (kSmemBudget - patch) / p.stage_bytes;
+  if (p.b_stationary) p.stage_bytes = 2 * kABytes;       // weights live in the resident region, stages carry activations only
+  else p.b_region_bytes = 0;
+  const int patch = tc_uses_patch(p.mode) ? kEpiPatchBytes : 0;   // 8 x 4 KB (correlation) or 16 x 2 KB (GRU q) patches
+  int nst = (kSmemBudget - patch - p.b_region_bytes) / p.stage_bytes;
   if (nst > 8) nst = 8;
   p.nstages = nst;
   int cols = 32;
   while (cols < 2 * p.bn) cols <<= 1;           // two accumulator buffers (ping-pong promotion)
   p.tmem_cols = cols;
   if (p.group_chunks <= 0) p.group_chunks = 2;
-  return nst * p.stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + patch;
+  return p.b_region_bytes + nst * p.stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + patch;
 }
 
-// Promotion/epilogue warps of the convolution instantiation: kEpiWarpsConv by default, RAFT_B200_EPI_WARPS=8|16 overrides.
-inline int tc_epi_warps() {
-  static int w = -1;
-  if (w < 0) {
-    const char* e = getenv("RAFT_B200_EPI_WARPS");
-    const int v = e ? atoi(e) : kEpiWarpsConv;
-    w = (v == 8) ? 8 : 16;
-  }
-  return w;
+// Resident-weights plan for a stride-any LINEAR convolution whose whole weight set fits beside >= 2 activation stages
+// and whose CTAs each process several tiles (otherwise streaming moves the same bytes).  Rebuilds p.b_map with a box
+// that spans all taps.  RAFT_B200_BSTAT=0 disables it (A/B timing), =2 forces it for small inputs (tests).  Call after bn, B, H, W, TH, TW, kh, kw, nseg,
+// seg_chunks are set and before tc_launch().
+inline int tc_try_stationary(TcConvParams& p, const __half* w_hi, const __half* w_lo, int cout_pad, int cin_pad) {
+  static const int enabled = [] { const char* e = getenv("RAFT_B200_BSTAT"); return e ? atoi(e) : 0; }();   // default off (measured slower); 1: on, 2: also for few tiles
+  p.b_stationary = 0;
+  p.b_region_bytes = 0;
+  if (!enabled || p.mode != EPI_LINEAR || p.nseg != 1 || p.bn != cout_pad || p.b_batch_stride != 0) return RAFT_OK;
+  const int taps = p.kh * p.kw, chunks = p.seg_chunks[0];
+  if (taps > 256 || chunks * kChunkK != cin_pad) return RAFT_OK;
+  const long bytes = (long)taps * chunks * 2 * p.bn * kChunkK * 2;
+  if (bytes > kSmemBudget - 2 * (2 * kABytes) || bytes >= (1 << 20)) return RAFT_OK;
+  const long mtiles = (long)p.B * ceil_div(p.H, p.TH) * ceil_div(p.W, p.TW);
+  if (mtiles < 2L * kNumSMs && enabled != 2) return RAFT_OK;
+  const ptrdiff_t pstride = reinterpret_cast<const char*>(w_lo) - reinterpret_cast<const char*>(w_hi);
+  if (pstride <= 0 || (pstride & 15)) return RAFT_ERR_BAD_ARG;
+  uint64_t dims[4] = {(uint64_t)cin_pad, (uint64_t)cout_pad, (uint64_t)taps, 2};
+  uint64_t str[3] = {(uint64_t)cin_pad * 2, (uint64_t)cout_pad * cin_pad * 2, (uint64_t)pstride};
+  uint32_t box[4] = {64, (uint32_t)p.bn, (uint32_t)taps, 2};
+  RAFT_TRY(make_tmap_f16(&p.b_map, w_hi, 4, dims, str, box));
+  p.b_stationary = 1;
+  p.b_region_bytes = (int)bytes;
+  return RAFT_OK;
 }
 
 // Preferred cluster size (1, 2 or 4); RAFT_B200_CLUSTER overrides the default of 2.
@@ -726,9 +952,9 @@ inline int tc_launch(TcConvParams& p, int n_tiles_n, cudaStream_t stream) {
   if (p.nstages < 2) return RAFT_ERR_UNSUPPORTED;
   static bool attr_set = false;   // benign race: idempotent
   if (!attr_set) {
-    RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<true, kEpiWarpsCorr>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<false, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<false, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<true, kEpiWarpsCorr, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   const int mtiles = p.B * p.tiles_y * p.tiles_x;
@@ -736,9 +962,9 @@ inline int tc_launch(TcConvParams& p, int n_tiles_n, cudaStream_t stream) {
   p.cluster = 1;
   const long ntiles = (long)mtiles * n_tiles_n;
   const unsigned grid = (unsigned)(ntiles < kNumSMs ? ntiles : kNumSMs);   // one persistent CTA per SM
-  if (p.mode == EPI_CORR) conv_tc_kernel<true, kEpiWarpsCorr><<<grid, 64 + 32 * kEpiWarpsCorr, smem, stream>>>(p);
-  else if (tc_epi_warps() == 8) conv_tc_kernel<false, 8><<<grid, 64 + 32 * 8, smem, stream>>>(p);
-  else conv_tc_kernel<false, 16><<<grid, 64 + 32 * 16, smem, stream>>>(p);
+  if (p.mode == EPI_CORR) conv_tc_kernel<true, kEpiWarpsCorr, false><<<grid, 64 + 32 * kEpiWarpsCorr, smem, stream>>>(p);
+  else if (p.mode == EPI_GRU_Q) conv_tc_kernel<false, kEpiWarpsConv, false><<<grid, 64 + 32 * kEpiWarpsConv, smem, stream>>>(p);
+  else conv_tc_kernel<false, kEpiWarpsConv, true><<<grid, 64 + 32 * kEpiWarpsConv, smem, stream>>>(p);
   return raft_launch_status();
 }
 

@@ -675,26 +675,32 @@ __global__ void stem_im2col_kernel(const float* __restrict__ img, int N, int H, 
     const int grp = (int)(i % 24);
     const size_t px = i / 24;
     const int x = (int)(px % w), y = (int)((px / w) % h), n = (int)(px / ((size_t)w * h));
-    uint32_t ph[4], pl[4];
+    uint32_t ph[4] = {0u, 0u, 0u, 0u}, pl[4] = {0u, 0u, 0u, 0u};
+    if (grp * 8 < 147) {
+      // channel kk = (window row ty) * 21 + j, and the 21 values j = 3 * (window column) + rgb of one window row are
+      // CONTIGUOUS in the NHWC image: walk (ty, j) incrementally instead of dividing per element.
+      int ty = (grp * 8) / 21, j = grp * 8 - ty * 21;
+      const int ix0 = 2 * x - pad_l;
+      const float* base = img + ((size_t)n * H * W + ix0) * 3;      // + iy * W * 3 + j  (only dereferenced in bounds)
+      float v[8];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      __half hh[2], ll[2];
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int kk = grp * 8 + 2 * e + u;
-        float v = 0.f;
-        if (kk < 147) {
-          const int tap = kk / 3, c = kk - tap * 3;
-          const int iy = 2 * y + tap / 7 - pad_t, ix = 2 * x + tap % 7 - pad_l;
-          if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
-            v = __ldg(img + (((size_t)n * H + iy) * W + ix) * 3 + c);
-            if (image_norm) v = __fsub_rn(__fmul_rn(2.0f, __fdiv_rn(v, 255.0f)), 1.0f);
-          }
+      for (int e = 0; e < 8; ++e) {
+        const int iy = 2 * y + ty - pad_t, ix = ix0 + ((j * 11) >> 5);   // j / 3 for j < 21
+        v[e] = 0.f;
+        if (ty < 7 && iy >= 0 && iy < H && ix >= 0 && ix < W) {
+          v[e] = __ldg(base + (ptrdiff_t)iy * W * 3 + j);
+          if (image_norm) v[e] = __fsub_rn(__fmul_rn(2.0f, __fdiv_rn(v[e], 255.0f)), 1.0f);
         }
-        split_f16(v, hh[u], ll[u]);
+        if (++j == 21) { j = 0; ++ty; }
       }
-      ph[e] = pack_h2(hh[0], hh[1]);
-      pl[e] = pack_h2(ll[0], ll[1]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        __half h0, l0, h1, l1;
+        split_f16(v[2 * e], h0, l0);
+        split_f16(v[2 * e + 1], h1, l1);
+        ph[e] = pack_h2(h0, h1);
+        pl[e] = pack_h2(l0, l1);
+      }
     }
     reinterpret_cast<uint4*>(hi)[i] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
     reinterpret_cast<uint4*>(lo)[i] = make_uint4(pl[0], pl[1], pl[2], pl[3]);

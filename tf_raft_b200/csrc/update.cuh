@@ -11,6 +11,7 @@ namespace raft {
 extern thread_local long long g_launches;
 extern int g_dbg_layer;            // timeline debugging (raft_b200_debug_timeline)
 extern long long* g_dbg_buf;
+extern int g_dbg_count;
 #define RAFT_COUNT_LAUNCH() (++::raft::g_launches)
 
 // ------------------------------------------------------------------------------------------------

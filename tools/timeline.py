@@ -19,7 +19,7 @@ blk([net, inp, corr, flow])
 torch.cuda.synchronize()
 _lib.lib().raft_b200_debug_timeline(-1, None)
 t = buf.cpu().numpy().reshape(4, 512)
-n_it = int((t[0] > 0).sum()); n_g = int((t[2] > 0).sum())
+n_it = int((t[0] > 0).sum()); n_g = int((t[2][:256] > 0).sum())   # rows 2/3: [0,256) epilogue-warp stamps, [256,512) issuer / per-tile
 t0 = t[0][0]
 print(f'layer {layer}: {n_it} chunks, {n_g} groups; cycles relative to first slot-free')
 print('chunk  slot_free  data_landed  (landed-free)')

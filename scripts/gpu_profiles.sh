@@ -25,13 +25,14 @@ python tools/timeline.py 4 > gpurun_out/timeline_zr1.log 2>&1
 for l in 0 5 8; do python tools/timeline.py $l 2>&1 | tail -n 1 >> gpurun_out/timeline_zr1.log; done
 python tools/timeline_enc.py 1 > gpurun_out/timeline_enc1.log 2>&1
 RAFT_B200_ENC_GROUP=2 timeout 200 python bench.py --steps 10 --warmup 3 --quick > gpurun_out/bench_r01_encgroup2.json 2> /dev/null; echo "bench encgroup2 exit $?"
+RAFT_B200_UPD_GROUP=3 timeout 200 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_r01_updgroup3.json 2> /dev/null; echo "bench updgroup3 exit $?"
 python - <<'PY'
 import json
-for f in ('bench_r01', 'bench_r01_fp32', 'bench_r01_reference'):
+for f in ('bench_r01', 'bench_r01_updgroup3', 'bench_r01_encgroup2'):
     try:
         d = json.load(open(f'gpurun_out/{f}.json'))
         print(f, {k: d.get(k) for k in ('value','ms_per_step','gpu_launches')}, 'e2e', d['e2e']['value'])
-        if 'parity' in d: print('  parity', {k: d['parity'][k] for k in ('max_abs','median_abs','frac_px_within_1e-3','iterations_within_1e-3')}, d['clocks'])
-        if 'roofline' in d: print('  roofline', d['roofline']['achieved'], d['roofline']['executed_frac'], '| corr', d['roofline_corr_lookup']['achieved'], d['roofline_corr_lookup']['ms'], '| cpu', d['cpu_baseline']['value'], d['cpu_baseline']['cores'])
+        if 'max_abs' in d.get('parity', {}): print('  parity', {k: d['parity'][k] for k in ('max_abs','median_abs','frac_px_within_1e-3','iterations_within_1e-3')}, d['clocks'])
+        if 'roofline' in d and d.get('cpu_baseline', {}).get('value'): print('  roofline', d['roofline']['achieved'], d['roofline']['executed_frac'], '| corr', d['roofline_corr_lookup']['achieved'], d['roofline_corr_lookup']['ms'], '| cpu', d['cpu_baseline']['value'], d['cpu_baseline']['cores'])
     except Exception as e: print(f, 'ERR', e)
 PY

@@ -274,6 +274,10 @@ inline int launch_tc_layer(const UpdateCtx& c, int layer, int nseg, const TcSeg*
   p.inv_scale = reinterpret_cast<const float*>(c.prepared + c.PL.tc_scale[layer]) + 1;
   if (p.out_scale == 0.0f) p.out_scale = 1.0f;
   if (g_dbg_layer == layer) p.dbg = g_dbg_buf;
+  {   // promotion group of the update-block layers (default 2, see conv_tc.cuh); RAFT_B200_UPD_GROUP overrides for experiments
+    static const int grp = [] { const char* e = getenv("RAFT_B200_UPD_GROUP"); return e ? atoi(e) : 0; }();
+    if (grp > 0) p.group_chunks = grp;
+  }
   RAFT_COUNT_LAUNCH();
   return tc_launch(p, ntn > 0 ? ntn : L.ntn, c.stream);
 }

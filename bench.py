@@ -309,7 +309,7 @@ def run_ours(args):
             'roofline': {'bound': 'tensor', 'kernel': 'conv_tc_kernel (update-block implicit GEMMs, 12 iterations)',
                          'achieved': ach_tflops, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
                          'frac': ach_tflops / peaks['bf16_tflops'],
-                         'traffic': {'bytes_per_launch': 31.6e6, 'launch': 'GRU z||r layer (14336 px x 256 x 1920)',
+                         'traffic': {'bytes_per_launch': 31.5e6, 'launch': 'GRU z||r layer (14336 px x 256 x 1920)',
                                      'source': 'profiles/r01_ncu_conv_tc.txt (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full; '
                                                'caches flushed by ncu -- operands are L2-resident in the real run)',
                                      'algorithmic_bytes_per_launch': 14336 * (384 * 5 * 4 + 256 * 4) + 256 * 1920 * 4},
@@ -321,7 +321,7 @@ def run_ours(args):
             'roofline_corr_lookup': {'bound': 'hbm', 'kernel': 'correlation pyramid build + 12 lookups',
                                      'achieved': ach_gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                                      'frac': ach_gbs / peaks['hbm_gbs'],
-                                     'traffic': {'lookup_bytes_per_launch': 48.8e6, 'lookup_algorithmic_bytes': B_PER_GPU * LOOKUP_BYTES_PER_PAIR_ITER,
+                                     'traffic': {'lookup_bytes_per_launch': 49.2e6, 'lookup_algorithmic_bytes': B_PER_GPU * LOOKUP_BYTES_PER_PAIR_ITER,
                                                  'source': 'profiles/r01_ncu_lookup.txt'},
                                      'ms': {'pyramid_build': t_corr * 1e3, 'lookup': t_lookup * 1e3},
                                      'peak_source': peaks['source']},

@@ -55,8 +55,6 @@ struct alignas(64) TcConvParams {
   int n_tiles_n;                  // column tiles (tile id = n_tile * pixel_tiles + pixel_tile)
   int nstages, stage_bytes, tmem_cols;
   int group_chunks;               // K chunks per promotion group (accumulation chain = 12 * group_chunks MMAs)
-  int cluster;                    // CTAs per cluster along the pixel-tile axis (1, 2, 4): the weight tile is loaded
-                                  // once per cluster -- each CTA fetches bn/cluster rows and multicasts them
   int b_batch_stride;             // B-map coordinate 2 = tap + b * b_batch_stride (correlation: 1, taps = 1)
   int mode, act;
   const float* bias;              // [n_total padded to bn multiple]; may be null
@@ -924,27 +922,6 @@ inline int tc_try_stationary(TcConvParams& p, const __half* w_hi, const __half* 
   return RAFT_OK;
 }
 
-// Preferred cluster size (1, 2 or 4); RAFT_B200_CLUSTER overrides the default of 2.
-inline int tc_cluster_pref() {
-  static int pref = -1;
-  if (pref < 0) {
-    const char* e = getenv("RAFT_B200_CLUSTER");
-    int v = e ? atoi(e) : 1;
-    pref = (v == 4 || v == 2) ? v : 1;
-  }
-  return pref;
-}
-
-// Cluster size for a launch: largest power of two <= preference that divides the pixel-tile count and keeps
-// the per-CTA weight slice a whole number of 8-row swizzle atoms.  Callers need it BEFORE building the weight
-// tensor maps, whose box is bn / cluster rows.
-inline int tc_plan_cluster(int B, int H, int W, int th, int tw, int bn) {
-  // Measured (profiles/): 2- and 4-CTA weight multicast did not beat unicast -- L2 already de-duplicates the
-  // identical weight requests of neighbouring SMs -- so the persistent kernel runs without clusters.
-  (void)B; (void)H; (void)W; (void)th; (void)tw; (void)bn;
-  return 1;
-}
-
 inline int tc_launch(TcConvParams& p, int n_tiles_n, cudaStream_t stream) {
   if (p.bn % 16 != 0 || p.bn < 16 || p.bn > 256 || p.TW * p.TH != kTileM) return RAFT_ERR_BAD_SHAPE;
   if (p.stride < 1) p.stride = 1;
@@ -959,7 +936,6 @@ inline int tc_launch(TcConvParams& p, int n_tiles_n, cudaStream_t stream) {
   }
   const int mtiles = p.B * p.tiles_y * p.tiles_x;
   p.n_tiles_n = n_tiles_n;
-  p.cluster = 1;
   const long ntiles = (long)mtiles * n_tiles_n;
   const unsigned grid = (unsigned)(ntiles < kNumSMs ? ntiles : kNumSMs);   // one persistent CTA per SM
   if (p.mode == EPI_CORR) conv_tc_kernel<true, kEpiWarpsCorr, false><<<grid, 64 + 32 * kEpiWarpsCorr, smem, stream>>>(p);

@@ -44,19 +44,6 @@ inline int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uin
   return r == CUDA_SUCCESS ? 0 : RAFT_ERR_DRIVER;
 }
 
-// NHWC fp16 activation plane [B][H][W][cstride] -> rank-4 map, box {64 ch, tw, th, 1}.
-// `stride` > 1 samples every stride-th pixel (TMA elementStrides): the box spans tw*stride x th*stride input
-// pixels and delivers tw x th of them -- the A operand of a strided convolution, still one TMA per tap.
-inline int make_tmap_act(CUtensorMap* out, const __half* base, int B, int H, int W, int cstride, int tw, int th,
-                         int stride = 1) {
-  uint64_t dims[4] = {(uint64_t)cstride, (uint64_t)W, (uint64_t)H, (uint64_t)B};
-  uint64_t str[3] = {(uint64_t)cstride * 2, (uint64_t)W * cstride * 2, (uint64_t)H * W * cstride * 2};
-  uint32_t box[4] = {64, (uint32_t)(tw * stride), (uint32_t)(th * stride), 1};
-  uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
-  if (tw * stride > 256 || th * stride > 256) return RAFT_ERR_BAD_SHAPE;
-  return make_tmap_f16(out, base, 4, dims, str, box, es);
-}
-
 // Measured on B200 (tools/tma_probe.cu): TMA delivery per SM is bound by the NUMBER of boxes (~616 cycles per box,
 // 16 KB or 32 KB alike, not improved by more boxes in flight).  The hi and lo planes of every operand are therefore
 // fetched by ONE box: the plane index is an extra tensor dimension whose stride is (lo - hi) bytes.
@@ -82,14 +69,6 @@ inline int make_tmap_wgt2(CUtensorMap* out, const __half* hi, const __half* lo, 
   uint64_t str[3] = {(uint64_t)cin_pad * 2, (uint64_t)cout_pad * cin_pad * 2, (uint64_t)pstride};
   uint32_t box[4] = {64, (uint32_t)bn, 1, 2};
   return make_tmap_f16(out, hi, 4, dims, str, box);
-}
-
-// Packed weights [taps][cout_pad][cin_pad] fp16 -> rank-3 map, box {64 ch, bn, 1}.
-inline int make_tmap_wgt(CUtensorMap* out, const __half* base, int taps, int cout_pad, int cin_pad, int bn) {
-  uint64_t dims[3] = {(uint64_t)cin_pad, (uint64_t)cout_pad, (uint64_t)taps};
-  uint64_t str[2] = {(uint64_t)cin_pad * 2, (uint64_t)cout_pad * cin_pad * 2};
-  uint32_t box[3] = {64, (uint32_t)bn, 1};
-  return make_tmap_f16(out, base, 3, dims, str, box);
 }
 
 }  // namespace raft

@@ -2,7 +2,7 @@
 daigo0927/tf-raft: `CorrBlock`, `BasicUpdateBlock` / `SmallUpdateBlock`, `RAFT` / `SmallRAFT`.
 
 Compute lives in libraft_b200.so (hand-written CUDA, C ABI in include/raft_b200.h); PyTorch supplies
-device memory, streams and the (not yet hand-written) encoders.  No CPU fallback.
+device memory, streams, CUDA graphs and torch.distributed.  No CPU fallback.
 """
 from . import _lib
 from .layers.corr import CorrBlock, bilinear_sampler, coords_grid, tfa_sampler, upflow8
@@ -10,6 +10,8 @@ from .layers.extractor import BasicEncoder, SmallEncoder
 from .layers.update import BasicUpdateBlock, SmallUpdateBlock
 from .losses import end_point_error, sequence_loss
 from .model import RAFT, SmallRAFT
+from .preprocess import CropOrPadder, pad_to_multiple, resize_with_crop_or_pad
 
 __all__ = ['CorrBlock', 'bilinear_sampler', 'coords_grid', 'tfa_sampler', 'upflow8', 'BasicEncoder', 'SmallEncoder',
-           'BasicUpdateBlock', 'SmallUpdateBlock', 'RAFT', 'SmallRAFT', 'sequence_loss', 'end_point_error']
+           'BasicUpdateBlock', 'SmallUpdateBlock', 'RAFT', 'SmallRAFT', 'sequence_loss', 'end_point_error',
+           'resize_with_crop_or_pad', 'CropOrPadder', 'pad_to_multiple']

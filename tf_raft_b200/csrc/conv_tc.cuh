@@ -73,6 +73,10 @@ struct alignas(64) TcConvParams {
   int b_stationary;      // 1: all weights of the layer stay resident in shared memory (loaded once per CTA)
   int b_region_bytes;    // bytes of that resident region (0 otherwise)
   long long* dbg;                          // optional timeline of CTA 0 (tools/timeline.py): [4][512] clock64 stamps
+  // kStats instantiation (encoder norms that need data statistics): the epilogue also reduces each warp's 32 rows to
+  // per-channel (n, mean, M2) partials, part[g][tile * 4 + quarter][{n, mean, M2}][n_total], merged by norm_final_kernel.
+  float* stats_part;
+  int stats_per_image;                     // 1: one statistics group per image (InstanceNorm); 0: one for the batch
 };
 
 #if defined(__CUDA_ARCH__)
@@ -531,6 +535,67 @@ __device__ __forceinline__ void tc_epilogue_t(const TcConvParams& p, float (&v)[
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Statistics epilogue (kStats): raw convolution output y = acc * inv_scale + bias to the fp32 plane, plus the
+// per-channel (n, mean, M2) of this warp's 32 rows, so that the InstanceNorm / training-BatchNorm statistics need no
+// second pass over y.  Two-pass in registers (mean first, then squared deviations): no E[x^2]-E[x]^2 cancellation.
+// ------------------------------------------------------------------------------------------------
+// Sums t[0..15] over the 32 lanes; afterwards lane L holds the total of element L & 15 (in t[0]).  31 shuffles: one
+// butterfly step on all 16 values, then four steps that each halve the number of live values.  Fixed order: deterministic.
+__device__ __forceinline__ float warp_reduce16(float (&t)[16], int lane) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) t[i] += __shfl_xor_sync(0xffffffffu, t[i], 16);
+#pragma unroll
+  for (int step = 0; step < 4; ++step) {
+    const int off = 8 >> step, cnt = 8 >> step;
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < cnt; ++i) {
+      const float send = up ? t[i] : t[i + cnt];
+      const float keep = up ? t[i + cnt] : t[i];
+      t[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return t[0];
+}
+
+__device__ __forceinline__ void tc_epilogue_stats(const TcConvParams& p, float (&v)[32], bool valid, size_t pix, int col,
+                                                  float inv_scale, float* __restrict__ part, int lane) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 bq = ldg4(p.bias + col + 4 * q);      // bias array is zero-padded past the last column
+    v[4 * q] = v[4 * q] * inv_scale + bq.x; v[4 * q + 1] = v[4 * q + 1] * inv_scale + bq.y;
+    v[4 * q + 2] = v[4 * q + 2] * inv_scale + bq.z; v[4 * q + 3] = v[4 * q + 3] * inv_scale + bq.w;
+  }
+  if (valid && col + 32 <= p.n_total) {                 // host guarantees n_total % 32 == 0 and 16-byte alignment
+    float* dst = p.out_f32 + pix * (size_t)p.f32_stride + p.f32_c0 + col;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) st4(dst + 4 * q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+  }
+  const float n = (float)__popc(__ballot_sync(0xffffffffu, valid));
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    float t[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) t[j] = valid ? v[half * 16 + j] : 0.0f;
+    const float sum = warp_reduce16(t, lane);
+    const float mean = n > 0.0f ? sum / n : 0.0f;       // lane L: channel col + half*16 + (L & 15)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float mj = __shfl_sync(0xffffffffu, mean, j);
+      const float d = valid ? v[half * 16 + j] - mj : 0.0f;
+      t[j] = d * d;
+    }
+    const float m2 = warp_reduce16(t, lane);
+    const int c = col + half * 16 + lane;
+    if (lane < 16 && c < p.n_total) {
+      part[c] = n;
+      part[p.n_total + c] = mean;
+      part[2 * p.n_total + c] = m2;
+    }
+  }
+}
+
 // Coalesced store of one 32x32 accumulator block of the correlation volume (patch = swizzled transposition buffer):
 // 8 lanes x 16 bytes cover a row, so a warp writes 4 full 128-byte pyramid rows per instruction.
 __device__ __noinline__ void tc_store_corr_block(const float* patch, long long pix_lane, float* out, int stride, int col0,
@@ -566,7 +631,7 @@ __device__ __noinline__ void tc_store_corr_block(const float* patch, long long p
 
 // kCorr selects the correlation epilogue at compile time so that its transposition path costs the convolution
 // instantiation neither registers nor code.
-template <bool kCorr, int kEpiWarps, bool kRowEpi>
+template <bool kCorr, int kEpiWarps, bool kRowEpi, bool kStats = false>
 __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_tc_kernel(const __grid_constant__ TcConvParams p) {
 #if defined(__CUDA_ARCH__)
   // Persistent: CTA c processes output tiles c, c + gridDim.x, ...  A tile is (pixel tile, column tile).  All
@@ -795,6 +860,17 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_tc_kernel(const _
                                   p.corr_div);
             }
           }
+        } else if constexpr (kStats) {     // raw output + statistics partials (see tc_epilogue_stats)
+          const bool valid = x < p.W && y < p.H;
+          const size_t pix = valid ? ((size_t)b * p.H + y) * p.W + x : 0;
+          const int tiles_img = p.tiles_y * p.tiles_x;
+          const int nsplit = (p.stats_per_image ? tiles_img : p.B * tiles_img) * 4;
+          const int tile_local = (p.stats_per_image ? 0 : b * tiles_img) + ty * p.tiles_x + tx;
+          float* part = p.stats_part + ((size_t)(p.stats_per_image ? b : 0) * nsplit + tile_local * 4 + quarter) * 3 * p.n_total;
+#pragma unroll
+          for (int ci = 0; ci < kMaxCh; ++ci) {
+            if (ci < my_chunks) tc_epilogue_stats(p, racc[ci], valid, pix, nt * p.bn + (chunk0 + ci) * 32, inv_scale, part, lane);
+          }
         } else if constexpr (kRowEpi) {    // convolution, thread-per-row register epilogue (EPI_LINEAR, EPI_GRU_ZR)
           if (x < p.W && y < p.H) {
             const size_t pix = ((size_t)b * p.H + y) * p.W + x;
@@ -931,6 +1007,7 @@ inline int tc_launch(TcConvParams& p, int n_tiles_n, cudaStream_t stream) {
   if (!attr_set) {
     RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<false, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<false, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<false, 16, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<true, kEpiWarpsCorr, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
@@ -940,6 +1017,11 @@ inline int tc_launch(TcConvParams& p, int n_tiles_n, cudaStream_t stream) {
   const unsigned grid = (unsigned)(ntiles < kNumSMs ? ntiles : kNumSMs);   // one persistent CTA per SM
   if (p.mode == EPI_CORR) conv_tc_kernel<true, kEpiWarpsCorr, false><<<grid, 64 + 32 * kEpiWarpsCorr, smem, stream>>>(p);
   else if (p.mode == EPI_GRU_Q) conv_tc_kernel<false, kEpiWarpsConv, false><<<grid, 64 + 32 * kEpiWarpsConv, smem, stream>>>(p);
+  else if (p.stats_part) {
+    if (p.mode != EPI_LINEAR || p.n_total % 32 != 0 || n_tiles_n != 1 || !p.out_f32 || ((p.f32_stride | p.f32_c0) & 3) || !p.bias)
+      return RAFT_ERR_UNSUPPORTED;
+    conv_tc_kernel<false, kEpiWarpsConv, true, true><<<grid, 64 + 32 * kEpiWarpsConv, smem, stream>>>(p);
+  }
   else conv_tc_kernel<false, kEpiWarpsConv, true><<<grid, 64 + 32 * kEpiWarpsConv, smem, stream>>>(p);
   return raft_launch_status();
 }

@@ -78,6 +78,7 @@ struct EncWs {
   float *X32, *O32, *Y32, *D32;
   __half *Xh, *Xl, *Oh, *Ol, *Fh, *Fl, *Ih, *Il;
   float *part, *mean, *mult;
+  float* part_tiles;     // fused statistics: (n, mean, M2) per (tile, TMEM lane quarter, channel), see conv_tc.cuh kStats
   size_t total;
 };
 constexpr int kNormSplit = 64;
@@ -106,6 +107,18 @@ inline EncWs enc_ws_layout(void* base, int variant, int N, int H, int W) {
     E.Ih = (__half*)take(np1 * 192 * 2); E.Il = (__half*)take(np1 * 192 * 2);
   }
   E.part = (float*)take((size_t)N * kNormSplit * 3 * 256 * 4);
+  {
+    // any 128-pixel tile shape covers an h x w plane with at most h*w/128 + h + w + 1 tiles
+    size_t cap = 0;
+    for (int l = 0; l < 3; ++l) {
+      const int d = 2 << l;
+      const size_t hl = (H + d - 1) / d, wl = (W + d - 1) / d;
+      const int c = l == 0 ? (S.c0 > S.c[0] ? S.c0 : S.c[0]) : S.c[l];
+      const size_t need = (size_t)N * (hl * wl / 128 + hl + wl + 1) * 4 * 3 * c;
+      if (need > cap) cap = need;
+    }
+    E.part_tiles = (float*)take(cap * 4);
+  }
   E.mean = (float*)take((size_t)N * 256 * 4);
   E.mult = (float*)take((size_t)N * 256 * 4);
   E.total = off;
@@ -185,9 +198,19 @@ struct EncCtx {
   const uint8_t* prep; EncLayout L; EncWs W; cudaStream_t st;
   int N, norm_type, stats;    // stats: 1 = statistics from the data (instance, or batch in training)
   int per_image;              // instance: one group per image; batch-training: one group
+  mutable int fused_nsplit;   // > 0: the last enc_conv_tc wrote this many statistics partials per group (fused statistics)
 };
 
+// Statistics of the encoder norms are either a separate pass over y (norm_stats_kernel) or -- RAFT_B200_FUSED_STATS=1,
+// not yet validated on hardware, default off -- partials written by the producing convolution's epilogue.
+inline bool enc_fused_stats() {
+  static const int v = [] { const char* e = getenv("RAFT_B200_FUSED_STATS"); return e ? atoi(e) : 0; }();
+  return v != 0;
+}
+
 // y (npix, C) raw conv output -> normalised, activated, (+skip), re-split.
+// c.fused_nsplit > 0: c.W.part_tiles already holds that many partials per statistics group, written by the
+// enc_conv_tc call that produced y.
 inline int enc_norm_apply(const EncCtx& c, const EncNormSlot& ns, const float* y, size_t npix, int P, int relu,
                           const float* skip32, const __half* skip_hi, const __half* skip_lo, float* out32, __half* hi,
                           __half* lo) {
@@ -195,11 +218,16 @@ inline int enc_norm_apply(const EncCtx& c, const EncNormSlot& ns, const float* y
   const int Pg = c.per_image ? P : (int)npix;
   const float* gamma = reinterpret_cast<const float*>(c.prep + ns.gamma);
   const float* beta = reinterpret_cast<const float*>(c.prep + ns.beta);
-  norm_stats_kernel<<<dim3((unsigned)G, kNormSplit), 256, 0, c.st>>>(y, Pg, C, kNormSplit, c.W.part);
-  norm_final_kernel<<<ceil_div(G * C * 32, 256), 256, 0, c.st>>>(c.W.part, G, C, kNormSplit, gamma, 1e-3f, c.W.mean, c.W.mult);
+  const bool fused = c.fused_nsplit > 0;
+  if (fused) {
+    norm_final_kernel<<<ceil_div(G * C * 32, 256), 256, 0, c.st>>>(c.W.part_tiles, G, C, c.fused_nsplit, gamma, 1e-3f, c.W.mean, c.W.mult);
+  } else {
+    norm_stats_kernel<<<dim3((unsigned)G, kNormSplit), 256, 0, c.st>>>(y, Pg, C, kNormSplit, c.W.part);
+    norm_final_kernel<<<ceil_div(G * C * 32, 256), 256, 0, c.st>>>(c.W.part, G, C, kNormSplit, gamma, 1e-3f, c.W.mean, c.W.mult);
+  }
   norm_apply_kernel<<<grid_for(npix * (pad64(C) / 8)), 256, 0, c.st>>>(y, npix, P, C, c.per_image, c.W.mean, c.W.mult, beta, relu,
                                                                  skip32, skip_hi, skip_lo, out32, hi, lo, pad64(C));
-  g_launches += 3;
+  g_launches += fused ? 2 : 3;
   return raft_launch_status();
 }
 
@@ -210,6 +238,7 @@ inline int enc_conv_tc(const EncCtx& c, const EncConvSlot& cs, const EncNormSlot
                        __half* ohi, __half* olo) {
   TcConvParams p;
   memset(&p, 0, sizeof(p));
+  c.fused_nsplit = 0;
   int tw, th;
   tc_pick_tile(Wout, Hout, &tw, &th);
   if (tw * stride > 256) tw = 128 / stride, th = 128 / tw;
@@ -242,6 +271,12 @@ inline int enc_conv_tc(const EncCtx& c, const EncConvSlot& cs, const EncNormSlot
     p.residual = skip; p.res_stride = cs.cout; p.res_c0 = 0;
   } else {
     p.act = ACT_NONE; p.out_hi = nullptr; p.out_lo = nullptr;
+    if (enc_fused_stats() && cs.cout % 32 == 0) {     // statistics partials from this convolution's epilogue
+      p.stats_part = c.W.part_tiles;
+      p.stats_per_image = c.per_image ? 1 : 0;
+      const int tiles = ceil_div(Hout, th) * ceil_div(Wout, tw);
+      c.fused_nsplit = (c.per_image ? tiles : c.N * tiles) * 4;
+    }
   }
   if (g_dbg_layer >= 1000 && g_dbg_count++ == g_dbg_layer - 1000) p.dbg = g_dbg_buf;   // timeline of the k-th encoder conv
   {

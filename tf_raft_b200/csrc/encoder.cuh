@@ -202,7 +202,7 @@ struct EncCtx {
 };
 
 // Statistics of the encoder norms are either a separate pass over y (norm_stats_kernel) or -- RAFT_B200_FUSED_STATS=1,
-// not yet validated on hardware, default off -- partials written by the producing convolution's epilogue.
+// parity-tested on hardware but not yet timed, default off -- partials written by the producing convolution's epilogue.
 inline bool enc_fused_stats() {
   static const int v = [] { const char* e = getenv("RAFT_B200_FUSED_STATS"); return e ? atoi(e) : 0; }();
   return v != 0;

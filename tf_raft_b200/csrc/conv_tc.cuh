@@ -80,12 +80,7 @@ struct alignas(64) TcConvParams {
 };
 
 #if defined(__CUDA_ARCH__)
-// ------------------------------------------------------------------------------------------------
-// Epilogue of one 32-column chunk of one pixel row.  Deliberately NOT inlined and written as rolled
-// loops over 4-element groups on a local-memory buffer: the fully unrolled multi-mode version was
-// 384 KB of SASS and instruction fetch ("no_instructions") became the top stall of every short-K layer.
-//   v[32]  accumulator values (in), pix = pixel index, col = first global output column, ncol = 32|16
-// ------------------------------------------------------------------------------------------------
+// 16-byte global accesses and the fast activation forms used by every epilogue.
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
@@ -93,167 +88,6 @@ __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<floa
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
 
-// Plain-value copy of the fields the epilogue needs.  The kernel parameter block is reached through a generic
-// pointer here, and without register copies every global store forces the compiler to re-load each field.
-struct EpiArgs {
-  int mode, act, n_total, hid, f32_stride, f32_c0, h_stride, h_c0, res_stride, res_c0, concat_n;
-  float out_scale, corr_div;
-  const float *bias, *post_scale, *post_shift, *residual, *concat_src;
-  float *out_f32, *z, *h;
-  __half *out_hi, *out_lo;
-};
-
-__device__ __noinline__ void tc_epilogue_chunk(const TcConvParams& pp, float* v, size_t pix, int col, int ncol,
-                                               float inv_scale) {
-  EpiArgs p;
-  p.mode = pp.mode; p.act = pp.act; p.n_total = pp.n_total; p.hid = pp.hid; p.f32_stride = pp.f32_stride;
-  p.f32_c0 = pp.f32_c0; p.h_stride = pp.h_stride; p.h_c0 = pp.h_c0; p.res_stride = pp.res_stride; p.res_c0 = pp.res_c0;
-  p.concat_n = pp.concat_n; p.out_scale = pp.out_scale; p.corr_div = pp.corr_div; p.bias = pp.bias;
-  p.post_scale = pp.post_scale; p.post_shift = pp.post_shift; p.residual = pp.residual; p.concat_src = pp.concat_src;
-  p.out_f32 = pp.out_f32; p.z = pp.z; p.h = pp.h; p.out_hi = pp.out_hi; p.out_lo = pp.out_lo;
-  // All loops are rolled (#pragma unroll 1) over groups of 4 columns with 16-byte accesses: every row of the
-  // tile is owned by one thread, so vector width -- not coalescing across lanes -- sets the memory efficiency.
-  if (p.mode == EPI_CORR) {
-    const int nvalid = min(ncol, p.n_total - col);
-    if (nvalid <= 0) return;
-    float* dst = p.out_f32 + pix * (size_t)p.f32_stride + col;
-    if (nvalid == 32 && (p.f32_stride & 3) == 0) {
-#pragma unroll 1
-      for (int q = 0; q < 8; ++q) {
-        const float4 a = ld4(v + 4 * q);
-        st4(dst + 4 * q, make_float4(__fdiv_rn(a.x, p.corr_div), __fdiv_rn(a.y, p.corr_div), __fdiv_rn(a.z, p.corr_div),
-                                     __fdiv_rn(a.w, p.corr_div)));
-      }
-    } else {
-#pragma unroll 1
-      for (int j = 0; j < nvalid; ++j) dst[j] = __fdiv_rn(v[j], p.corr_div);
-    }
-    return;
-  }
-
-  // bias (+ folded BatchNorm affine); the bias / affine arrays are zero-padded past the last column
-#pragma unroll 1
-  for (int q = 0; q < 8; ++q) {
-    float4 t = ld4(v + 4 * q);
-    t.x *= inv_scale; t.y *= inv_scale; t.z *= inv_scale; t.w *= inv_scale;
-    if (p.bias) {
-      const float4 b = ldg4(p.bias + col + 4 * q);
-      t.x += b.x; t.y += b.y; t.z += b.z; t.w += b.w;
-    }
-    if (p.post_scale) {
-      const float4 sc = ldg4(p.post_scale + col + 4 * q), sh = ldg4(p.post_shift + col + 4 * q);
-      t.x = t.x * sc.x + sh.x; t.y = t.y * sc.y + sh.y; t.z = t.z * sc.z + sh.z; t.w = t.w * sc.w + sh.w;
-    }
-    st4(v + 4 * q, t);
-  }
-
-  __half* dhi = nullptr;
-  __half* dlo = nullptr;
-  if (p.mode == EPI_LINEAR) {
-    const bool full = col + 32 <= p.n_total;       // chunk entirely inside the valid columns (the common case)
-    if (full) {
-      const float* res = p.residual ? p.residual + pix * (size_t)p.res_stride + p.res_c0 + col : nullptr;
-      const bool res_vec = ((p.res_stride | p.res_c0) & 3) == 0;
-#pragma unroll 1
-      for (int q = 0; q < 8; ++q) {
-        float4 t = ld4(v + 4 * q);
-        if (p.act == ACT_RELU) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
-        t.x *= p.out_scale; t.y *= p.out_scale; t.z *= p.out_scale; t.w *= p.out_scale;
-        if (res) {
-          float4 r;
-          if (res_vec) r = ldg4(res + 4 * q);
-          else r = make_float4(__ldg(res + 4 * q), __ldg(res + 4 * q + 1), __ldg(res + 4 * q + 2), __ldg(res + 4 * q + 3));
-          t.x = fmaxf(t.x + r.x, 0.f); t.y = fmaxf(t.y + r.y, 0.f); t.z = fmaxf(t.z + r.z, 0.f); t.w = fmaxf(t.w + r.w, 0.f);
-        }
-        st4(v + 4 * q, t);
-      }
-    } else {
-#pragma unroll 1
-      for (int j = 0; j < 32; ++j) {
-        float t = v[j];
-        if (p.act == ACT_RELU) t = fmaxf(t, 0.0f);
-        t *= p.out_scale;
-        if (col + j >= p.n_total) {                // padded columns: concat tail, else exact zeros
-          const int cj = col + j - p.n_total;
-          t = (p.concat_src && cj < p.concat_n) ? __ldg(p.concat_src + pix * p.concat_n + cj) : 0.0f;
-        } else if (p.residual) {
-          t = fmaxf(t + __ldg(p.residual + pix * (size_t)p.res_stride + p.res_c0 + col + j), 0.0f);
-        }
-        v[j] = t;
-      }
-    }
-    if (p.out_f32) {
-      const int nvalid = min(ncol, p.n_total - col);
-      float* dst = p.out_f32 + pix * (size_t)p.f32_stride + p.f32_c0 + col;
-      if (nvalid == 32 && ((p.f32_stride | p.f32_c0) & 3) == 0) {
-#pragma unroll 1
-        for (int q = 0; q < 8; ++q) st4(dst + 4 * q, ld4(v + 4 * q));
-      } else {
-#pragma unroll 1
-        for (int j = 0; j < nvalid; ++j) dst[j] = v[j];
-      }
-    }
-    if (p.out_hi && ncol == 32) {
-      const size_t o = pix * (size_t)p.h_stride + p.h_c0 + col;
-      dhi = p.out_hi + o;
-      dlo = p.out_lo + o;
-    }
-  } else if (p.mode == EPI_GRU_ZR) {
-    if (col < p.hid) {                              // z gate -> fp32 plane
-      float* dst = p.z + pix * (size_t)p.hid + col;
-#pragma unroll 1
-      for (int q = 0; q < 8; ++q) {
-        const float4 a = ld4(v + 4 * q);
-        st4(dst + 4 * q, make_float4(fast_sigmoid(a.x), fast_sigmoid(a.y), fast_sigmoid(a.z), fast_sigmoid(a.w)));
-      }
-    } else {                                        // r gate -> r*h, re-split for the q convolution
-      const int hc = col - p.hid;
-      const float* hp = p.h + pix * (size_t)p.hid + hc;
-#pragma unroll 1
-      for (int q = 0; q < 8; ++q) {
-        const float4 a = ld4(v + 4 * q), hv = ldg4(hp + 4 * q);
-        st4(v + 4 * q, make_float4(fast_sigmoid(a.x) * hv.x, fast_sigmoid(a.y) * hv.y, fast_sigmoid(a.z) * hv.z,
-                                   fast_sigmoid(a.w) * hv.w));
-      }
-      const size_t o = pix * (size_t)p.h_stride + p.h_c0 + hc;
-      dhi = p.out_hi + o;
-      dlo = p.out_lo + o;
-    }
-  } else {                                          // EPI_GRU_Q: h = (1-z)*h + z*tanh(v), in place
-    float* hrow = p.h + pix * (size_t)p.hid + col;
-    const float* zp = p.z + pix * (size_t)p.hid + col;
-#pragma unroll 1
-    for (int q = 0; q < 8; ++q) {
-      const float4 a = ld4(v + 4 * q), zv = ldg4(zp + 4 * q), hv = ld4(hrow + 4 * q);
-      const float4 hn = make_float4((1.0f - zv.x) * hv.x + zv.x * fast_tanh(a.x), (1.0f - zv.y) * hv.y + zv.y * fast_tanh(a.y),
-                                    (1.0f - zv.z) * hv.z + zv.z * fast_tanh(a.z), (1.0f - zv.w) * hv.w + zv.w * fast_tanh(a.w));
-      st4(v + 4 * q, hn);
-      st4(hrow + 4 * q, hn);
-    }
-    const size_t o = pix * (size_t)p.h_stride + p.h_c0 + col;
-    dhi = p.out_hi + o;
-    dlo = p.out_lo + o;
-  }
-
-  if (dhi) {                                        // fp16 hi/lo re-split, 8 channels (16 bytes) per store
-#pragma unroll 1
-    for (int q = 0; q < 4; ++q) {
-      const float4 a = ld4(v + 8 * q), b = ld4(v + 8 * q + 4);
-      const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-      uint32_t ph[4], pl[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        __half h0, l0, h1, l1;
-        split_f16(f[2 * e], h0, l0);
-        split_f16(f[2 * e + 1], h1, l1);
-        ph[e] = pack_h2(h0, h1);
-        pl[e] = pack_h2(l0, l1);
-      }
-      reinterpret_cast<uint4*>(dhi)[q] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-      reinterpret_cast<uint4*>(dlo)[q] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-    }
-  }
-}
 // ------------------------------------------------------------------------------------------------
 // Register-resident epilogue of one 32-column chunk of one pixel row (thread == row).
 //
@@ -394,7 +228,7 @@ __device__ __forceinline__ void tc_epilogue_regs(const TcConvParams& p, float (&
 }
 
 // ------------------------------------------------------------------------------------------------
-// Coalesced epilogue of a 32-row x 16-column accumulator block, AFTER transposition through shared memory:
+// Coalesced GRU-q epilogue of a 32-row x 16-column accumulator block, AFTER transposition through shared memory:
 // lane l holds rows (l>>2) + 8k (k = 0..3) and columns col .. col+3 of the block, so every global access of a warp
 // touches 8 rows x 64 contiguous bytes instead of 32 rows x 16 bytes.  Measured on the thread-per-row form: the LSU
 // retires about one distinct 128-byte line per cycle, which made the epilogue of a 256-column tile cost 14-22 k cycles.
@@ -416,8 +250,7 @@ __device__ __forceinline__ void store_split4(__half* hi, __half* lo, size_t o, b
   }
 }
 
-template <int MODE>
-__device__ __forceinline__ void tc_epilogue_t(const TcConvParams& p, float (&v)[4][4], const int (&pixr)[4], int col,
+__device__ __forceinline__ void tc_epilogue_q_t(const TcConvParams& p, float (&v)[4][4], const int (&pixr)[4], int col,
                                               float inv_scale) {
   if (p.bias) {
     const float4 bq = ldg4(p.bias + col);            // bias / affine arrays are zero-padded past the last column
@@ -433,83 +266,8 @@ __device__ __forceinline__ void tc_epilogue_t(const TcConvParams& p, float (&v)[
       for (int e = 0; e < 4; ++e) v[k][e] *= inv_scale;
   }
 
-  if (MODE == EPI_LINEAR) {
-    if (p.post_scale) {                                // folded BatchNorm / InstanceNorm affine
-      const float4 sc = ldg4(p.post_scale + col), sh = ldg4(p.post_shift + col);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        v[k][0] = v[k][0] * sc.x + sh.x; v[k][1] = v[k][1] * sc.y + sh.y;
-        v[k][2] = v[k][2] * sc.z + sh.z; v[k][3] = v[k][3] * sc.w + sh.w;
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        if (p.act == ACT_RELU) v[k][e] = fmaxf(v[k][e], 0.0f);
-        v[k][e] *= p.out_scale;
-      }
-    const int nvalid = p.n_total - col;                // real output columns among my 4
-    const bool res_vec = ((p.res_stride | p.res_c0) & 3) == 0;
-    const bool f32_vec = ((p.f32_stride | p.f32_c0) & 3) == 0;
-    const bool h_vec = ((p.h_stride | p.h_c0) & 3) == 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (pixr[k] < 0) continue;
-      const size_t pix = (size_t)pixr[k];
-      if (nvalid >= 4) {
-        if (p.residual) {
-          const float* rp = p.residual + pix * (size_t)p.res_stride + p.res_c0 + col;
-          if (res_vec) {
-            const float4 r4 = ldg4(rp);
-            v[k][0] = fmaxf(v[k][0] + r4.x, 0.f); v[k][1] = fmaxf(v[k][1] + r4.y, 0.f);
-            v[k][2] = fmaxf(v[k][2] + r4.z, 0.f); v[k][3] = fmaxf(v[k][3] + r4.w, 0.f);
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) v[k][e] = fmaxf(v[k][e] + __ldg(rp + e), 0.f);
-          }
-        }
-      } else {                                         // ragged tail: concatenated columns / zero padding
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int cj = e - nvalid;
-          if (cj >= 0) v[k][e] = (p.concat_src && cj < p.concat_n) ? __ldg(p.concat_src + pix * p.concat_n + cj) : 0.0f;
-          else if (p.residual) v[k][e] = fmaxf(v[k][e] + __ldg(p.residual + pix * (size_t)p.res_stride + p.res_c0 + col + e), 0.0f);
-        }
-      }
-      if (p.out_f32 && nvalid > 0) {
-        float* dst = p.out_f32 + pix * (size_t)p.f32_stride + p.f32_c0 + col;
-        if (nvalid >= 4 && f32_vec) st4(dst, make_float4(v[k][0], v[k][1], v[k][2], v[k][3]));
-        else {
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            if (e < nvalid) dst[e] = v[k][e];
-        }
-      }
-      if (p.out_hi) store_split4(p.out_hi, p.out_lo, pix * (size_t)p.h_stride + p.h_c0 + col, h_vec, v[k]);
-    }
-  } else if (MODE == EPI_GRU_ZR) {
-    const bool h_vec = ((p.h_stride | p.h_c0) & 3) == 0;
-    if (col < p.hid) {                                 // z gate -> fp32 plane
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (pixr[k] >= 0)
-          st4(p.z + (size_t)pixr[k] * p.hid + col,
-              make_float4(fast_sigmoid(v[k][0]), fast_sigmoid(v[k][1]), fast_sigmoid(v[k][2]), fast_sigmoid(v[k][3])));
-    } else {                                           // r gate -> r*h, re-split for the q convolution
-      const int hc = col - p.hid;
-      float4 hv[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) hv[k] = pixr[k] >= 0 ? ldg4(p.h + (size_t)pixr[k] * p.hid + hc) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (pixr[k] < 0) continue;
-        v[k][0] = fast_sigmoid(v[k][0]) * hv[k].x; v[k][1] = fast_sigmoid(v[k][1]) * hv[k].y;
-        v[k][2] = fast_sigmoid(v[k][2]) * hv[k].z; v[k][3] = fast_sigmoid(v[k][3]) * hv[k].w;
-        store_split4(p.out_hi, p.out_lo, (size_t)pixr[k] * p.h_stride + p.h_c0 + hc, h_vec, v[k]);
-      }
-    }
-  } else if (MODE == EPI_GRU_Q) {                      // h = (1-z)*h + z*tanh(v), in place
+  // h = (1-z)*h + z*tanh(v), in place
+  {
     const bool h_vec = ((p.h_stride | p.h_c0) & 3) == 0;
 #pragma unroll
     for (int k0 = 0; k0 < 4; k0 += 2) {                // two rows at a time: loads in flight together, registers bounded
@@ -913,7 +671,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_tc_kernel(const _
                     v[k][0] = t4.x; v[k][1] = t4.y; v[k][2] = t4.z; v[k][3] = t4.w;
                   }
                   const int col = nt * p.bn + c0 + 4 * c4;
-                  tc_epilogue_t<EPI_GRU_Q>(p, v, pixr, col, inv_scale);
+                  tc_epilogue_q_t(p, v, pixr, col, inv_scale);
                 }
               }
             }

@@ -77,6 +77,16 @@ struct alignas(64) TcConvParams {
   // per-channel (n, mean, M2) partials, part[g][tile * 4 + quarter][{n, mean, M2}][n_total], merged by norm_final_kernel.
   float* stats_part;
   int stats_per_image;                     // 1: one statistics group per image (InstanceNorm); 0: one for the batch
+  // kSwap instantiation (narrow layers, cout <= 128): operands exchanged -- the weights are the M operand (TMEM lane ==
+  // output channel, 128 slots, rows past cout_pad zero-filled by TMA) and a 256-pixel tile is the N operand (TMEM column
+  // == pixel).  One 32 KB weight box then serves 256 pixels instead of 128, and the epilogue is coalesced for free: for a
+  // given pixel the 32 lanes of a warp hold 32 consecutive channels.  TH * TW = 256, bn = 256.
+  int swap;
+  int cout;                                // real output channels (swap only)
+  // Programmatic dependent launch (RAFT_B200_PDL=1, experiment): the launch carries the programmatic-serialization
+  // attribute, so this grid's CTAs may be scheduled -- and run their prologue -- while the previous kernel in the stream
+  // drains; every thread then executes griddepcontrol.wait before touching global memory.
+  int pdl;
 };
 
 #if defined(__CUDA_ARCH__)
@@ -389,7 +399,7 @@ __device__ __noinline__ void tc_store_corr_block(const float* patch, long long p
 
 // kCorr selects the correlation epilogue at compile time so that its transposition path costs the convolution
 // instantiation neither registers nor code.
-template <bool kCorr, int kEpiWarps, bool kRowEpi, bool kStats = false>
+template <bool kCorr, int kEpiWarps, bool kRowEpi, bool kStats = false, bool kSwap = false>
 __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_tc_kernel(const __grid_constant__ TcConvParams p) {
 #if defined(__CUDA_ARCH__)
   // Persistent: CTA c processes output tiles c, c + gridDim.x, ...  A tile is (pixel tile, column tile).  All
@@ -447,6 +457,12 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_tc_kernel(const _
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  if (p.pdl) {
+    // barriers, TMEM and tensor-map prefetch above touch no global data; from here on the previous grid's results are
+    // read (and its inputs overwritten), so wait for it, then let the next grid in the stream start its own prologue.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  }
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -483,8 +499,13 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_tc_kernel(const _
               mbar_arrive_expect_tx(&full_bar[s], (uint32_t)p.stage_bytes);
               const int c = p.seg_c0[seg] + ch * kChunkK;
               // two boxes per stage: [A_hi | A_lo] and [B_hi | B_lo] (TMA cost is per box, not per byte)
-              tma_load_5d(st, &p.a_map[seg], &full_bar[s], c, x0 + dx, y0 + dy, b, 0);
-              if (!p.b_stationary) tma_load_4d(st + 2 * kABytes, &p.b_map, &full_bar[s], kc * kChunkK, n0, tcoord, 0);
+              if constexpr (kSwap) {   // weights -> M-operand slot (128 rows x 2 planes), 256 pixels -> N-operand slot
+                tma_load_4d(st, &p.b_map, &full_bar[s], kc * kChunkK, 0, tcoord, 0);
+                tma_load_5d(st + 2 * kABytes, &p.a_map[seg], &full_bar[s], c, x0 + dx, y0 + dy, b, 0);
+              } else {
+                tma_load_5d(st, &p.a_map[seg], &full_bar[s], c, x0 + dx, y0 + dy, b, 0);
+                if (!p.b_stationary) tma_load_4d(st + 2 * kABytes, &p.b_map, &full_bar[s], kc * kChunkK, n0, tcoord, 0);
+              }
             }
           }
         }
@@ -542,8 +563,8 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_tc_kernel(const _
   } else {
     // ===================== promotion + epilogue (warps 2..9) =====================
     const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
-    const int part = (warp - 2) >> 2;                // column slice of this warp within its lane quarter
-    const int chunk0 = part * chunks_per_part;
+    const int part_id = (warp - 2) >> 2;             // column slice of this warp within its lane quarter
+    const int chunk0 = part_id * chunks_per_part;
     const int my_chunks = max(0, min(chunks_per_part, nchunks32 - chunk0));
     const int m = quarter * 32 + lane;               // tile row == TMEM lane
     const int xl = m % p.TW, yl = m / p.TW;
@@ -616,6 +637,85 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_tc_kernel(const _
               __syncwarp();
               tc_store_corr_block(patch, pix_lane, p.out_f32, p.f32_stride, nt * p.bn + c0, p.bn - c0, p.n_total, p.corr_mul,
                                   p.corr_div);
+            }
+          }
+        } else if constexpr (kSwap) {      // operands exchanged: this thread = output channel m, columns = 256 pixels
+          const int ch = m;
+          const bool ch_ok = ch < p.cout;
+          const float bias = (ch_ok && p.bias) ? __ldg(p.bias + ch) : 0.0f;
+          const int tshift = 31 - __clz(p.TW);                         // TW is a power of two
+          const int px0 = tx * p.TW, py0 = ty * p.TH;
+#pragma unroll
+          for (int ci = 0; ci < kMaxCh; ++ci)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) racc[ci][j] = racc[ci][j] * inv_scale + bias;
+          if (p.stats_part) {
+            // raw output + this channel's (n, mean, M2) over the warp-slice's 64 pixels: two passes over registers
+            float n = 0.0f, sum = 0.0f;
+#pragma unroll
+            for (int ci = 0; ci < kMaxCh; ++ci) {
+              if (ci < my_chunks) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  const int mm = (chunk0 + ci) * 32 + j;
+                  const int xx = px0 + (mm & (p.TW - 1)), yy = py0 + (mm >> tshift);
+                  if (xx < p.W && yy < p.H) {
+                    n += 1.0f;
+                    sum += racc[ci][j];
+                    if (ch_ok) p.out_f32[(((size_t)b * p.H + yy) * p.W + xx) * p.f32_stride + p.f32_c0 + ch] = racc[ci][j];
+                  }
+                }
+              }
+            }
+            const float mean = n > 0.0f ? sum / n : 0.0f;
+            float m2 = 0.0f;
+#pragma unroll
+            for (int ci = 0; ci < kMaxCh; ++ci) {
+              if (ci < my_chunks) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  const int mm = (chunk0 + ci) * 32 + j;
+                  const int xx = px0 + (mm & (p.TW - 1)), yy = py0 + (mm >> tshift);
+                  const float d = racc[ci][j] - mean;
+                  if (xx < p.W && yy < p.H) m2 += d * d;
+                }
+              }
+            }
+            if (ch_ok) {
+              const int tiles_img = p.tiles_y * p.tiles_x;
+              const int nsplit = (p.stats_per_image ? tiles_img : p.B * tiles_img) * 4;
+              const int tile_local = (p.stats_per_image ? 0 : b * tiles_img) + ty * p.tiles_x + tx;
+              float* part = p.stats_part + ((size_t)(p.stats_per_image ? b : 0) * nsplit + tile_local * 4 + part_id) * 3 * p.cout;
+              part[ch] = n;
+              part[p.cout + ch] = mean;
+              part[2 * p.cout + ch] = m2;
+            }
+          } else if (ch_ok) {
+            const float psc = p.post_scale ? __ldg(p.post_scale + ch) : 1.0f;
+            const float psh = p.post_scale ? __ldg(p.post_shift + ch) : 0.0f;
+#pragma unroll
+            for (int ci = 0; ci < kMaxCh; ++ci) {
+              if (ci < my_chunks) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  const int mm = (chunk0 + ci) * 32 + j;
+                  const int xx = px0 + (mm & (p.TW - 1)), yy = py0 + (mm >> tshift);
+                  if (xx < p.W && yy < p.H) {
+                    const size_t pix = ((size_t)b * p.H + yy) * p.W + xx;
+                    float v = racc[ci][j] * psc + psh;
+                    if (p.act == ACT_RELU) v = fmaxf(v, 0.0f);
+                    v *= p.out_scale;
+                    if (p.residual) v = fmaxf(v + __ldg(p.residual + pix * (size_t)p.res_stride + p.res_c0 + ch), 0.0f);
+                    if (p.out_f32) p.out_f32[pix * (size_t)p.f32_stride + p.f32_c0 + ch] = v;
+                    if (p.out_hi) {
+                      __half hh, ll;
+                      split_f16(v, hh, ll);
+                      p.out_hi[pix * (size_t)p.h_stride + p.h_c0 + ch] = hh;
+                      p.out_lo[pix * (size_t)p.h_stride + p.h_c0 + ch] = ll;
+                    }
+                  }
+                }
+              }
             }
           }
         } else if constexpr (kStats) {     // raw output + statistics partials (see tc_epilogue_stats)
@@ -711,6 +811,22 @@ inline void tc_pick_tile(int W, int H, int* tw, int* th) {
   }
 }
 
+// 256-pixel tile of the kSwap instantiation: TW a power of two, TW * TH = 256, both box extents (x stride) <= 256.
+inline bool tc_pick_tile256(int W, int H, int stride, int* tw, int* th) {
+  long best = -1;
+  for (int t = 256; t >= 1; t >>= 1) {
+    const int hh = 256 / t;
+    if (t * stride > 256 || hh * stride > 256) continue;
+    const long area = (long)round_up(W, t) * round_up(H, hh);
+    if (best < 0 || area < best) {
+      best = area;
+      *tw = t;
+      *th = hh;
+    }
+  }
+  return best >= 0;
+}
+
 // Fills the derived launch fields (tile grid, stages, TMEM columns) of `p`; returns bytes of
 // dynamic shared memory.  Caller has set bn, B, H, W, TH, TW.
 inline int tc_finalize(TcConvParams& p) {
@@ -757,7 +873,9 @@ inline int tc_try_stationary(TcConvParams& p, const __half* w_hi, const __half* 
 }
 
 inline int tc_launch(TcConvParams& p, int n_tiles_n, cudaStream_t stream) {
-  if (p.bn % 16 != 0 || p.bn < 16 || p.bn > 256 || p.TW * p.TH != kTileM) return RAFT_ERR_BAD_SHAPE;
+  if (p.bn % 16 != 0 || p.bn < 16 || p.bn > 256 || p.TW * p.TH != (p.swap ? 256 : kTileM)) return RAFT_ERR_BAD_SHAPE;
+  if (p.swap && (p.bn != 256 || p.mode != EPI_LINEAR || n_tiles_n != 1 || p.cout < 1 || p.cout > kTileM || (p.TW & (p.TW - 1))))
+    return RAFT_ERR_UNSUPPORTED;
   if (p.stride < 1) p.stride = 1;
   const int smem = tc_finalize(p);
   if (p.nstages < 2) return RAFT_ERR_UNSUPPORTED;
@@ -766,6 +884,7 @@ inline int tc_launch(TcConvParams& p, int n_tiles_n, cudaStream_t stream) {
     RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<false, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<false, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<false, 16, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<false, 16, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<true, kEpiWarpsCorr, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
@@ -773,14 +892,37 @@ inline int tc_launch(TcConvParams& p, int n_tiles_n, cudaStream_t stream) {
   p.n_tiles_n = n_tiles_n;
   const long ntiles = (long)mtiles * n_tiles_n;
   const unsigned grid = (unsigned)(ntiles < kNumSMs ? ntiles : kNumSMs);   // one persistent CTA per SM
-  if (p.mode == EPI_CORR) conv_tc_kernel<true, kEpiWarpsCorr, false><<<grid, 64 + 32 * kEpiWarpsCorr, smem, stream>>>(p);
-  else if (p.mode == EPI_GRU_Q) conv_tc_kernel<false, kEpiWarpsConv, false><<<grid, 64 + 32 * kEpiWarpsConv, smem, stream>>>(p);
-  else if (p.stats_part) {
-    if (p.mode != EPI_LINEAR || p.n_total % 32 != 0 || n_tiles_n != 1 || !p.out_f32 || ((p.f32_stride | p.f32_c0) & 3) || !p.bias)
-      return RAFT_ERR_UNSUPPORTED;
-    conv_tc_kernel<false, kEpiWarpsConv, true, true><<<grid, 64 + 32 * kEpiWarpsConv, smem, stream>>>(p);
+  static const int pdl = [] { const char* e = getenv("RAFT_B200_PDL"); return e ? atoi(e) : 0; }();
+  p.pdl = pdl ? 1 : 0;
+  if (p.stats_part && !p.swap &&
+      (p.mode != EPI_LINEAR || p.n_total % 32 != 0 || n_tiles_n != 1 || !p.out_f32 || ((p.f32_stride | p.f32_c0) & 3) || !p.bias))
+    return RAFT_ERR_UNSUPPORTED;
+  const int threads = 64 + 32 * (p.mode == EPI_CORR ? kEpiWarpsCorr : kEpiWarpsConv);
+  if (!p.pdl) {
+    if (p.mode == EPI_CORR) conv_tc_kernel<true, kEpiWarpsCorr, false><<<grid, threads, smem, stream>>>(p);
+    else if (p.mode == EPI_GRU_Q) conv_tc_kernel<false, kEpiWarpsConv, false><<<grid, threads, smem, stream>>>(p);
+    else if (p.swap) conv_tc_kernel<false, kEpiWarpsConv, true, false, true><<<grid, threads, smem, stream>>>(p);
+    else if (p.stats_part) conv_tc_kernel<false, kEpiWarpsConv, true, true><<<grid, threads, smem, stream>>>(p);
+    else conv_tc_kernel<false, kEpiWarpsConv, true><<<grid, threads, smem, stream>>>(p);
+  } else {                                           // experiment: same kernels with the programmatic-serialization attribute
+    void (*kern)(TcConvParams) = conv_tc_kernel<false, kEpiWarpsConv, true>;
+    if (p.mode == EPI_CORR) kern = conv_tc_kernel<true, kEpiWarpsCorr, false>;
+    else if (p.mode == EPI_GRU_Q) kern = conv_tc_kernel<false, kEpiWarpsConv, false>;
+    else if (p.swap) kern = conv_tc_kernel<false, kEpiWarpsConv, true, false, true>;
+    else if (p.stats_part) kern = conv_tc_kernel<false, kEpiWarpsConv, true, true>;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    RAFT_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p));
   }
-  else conv_tc_kernel<false, kEpiWarpsConv, true><<<grid, 64 + 32 * kEpiWarpsConv, smem, stream>>>(p);
   return raft_launch_status();
 }
 

@@ -242,9 +242,22 @@ inline int enc_conv_tc(const EncCtx& c, const EncConvSlot& cs, const EncNormSlot
   int tw, th;
   tc_pick_tile(Wout, Hout, &tw, &th);
   if (tw * stride > 256) tw = 128 / stride, th = 128 / tw;
+  // Narrow layers (cout <= 128) with many tiles: exchange the operands (conv_tc.cuh kSwap) so that one weight box serves a
+  // 256-pixel tile.  RAFT_B200_ENC_SWAP=1 (2: regardless of the tile count, for small test inputs); default off -- compiled,
+  // not yet run on hardware.
+  bool swap = false;
+  {
+    static const int flag = [] { const char* e = getenv("RAFT_B200_ENC_SWAP"); return e ? atoi(e) : 0; }();
+    int tw2, th2;
+    if (flag && cs.cout <= kTileM && tc_pick_tile256(Wout, Hout, stride, &tw2, &th2)) {
+      const long mt2 = (long)c.N * ceil_div(Hout, th2) * ceil_div(Wout, tw2);
+      if (flag == 2 || mt2 >= 2L * kNumSMs) { swap = true; tw = tw2; th = th2; }
+    }
+  }
   RAFT_TRY(make_tmap_act2(&p.a_map[0], ahi, alo, c.N, Hin, Win, cs.cin_pad, tw, th, stride));
   RAFT_TRY(make_tmap_wgt2(&p.b_map, reinterpret_cast<const __half*>(c.prep + cs.hi),
-                          reinterpret_cast<const __half*>(c.prep + cs.lo), cs.kh * cs.kw, cs.cout_pad, cs.cin_pad, cs.cout_pad));
+                          reinterpret_cast<const __half*>(c.prep + cs.lo), cs.kh * cs.kw, cs.cout_pad, cs.cin_pad,
+                          swap ? kTileM : cs.cout_pad));
   p.nseg = 1; p.seg_chunks[0] = cs.cin_pad / kChunkK; p.seg_c0[0] = 0;
   p.kh = cs.kh; p.kw = cs.kw; p.stride = stride;
   // Keras 'same': stride 1 -> (k-1)/2 before; stride 2 on even input -> total k-2, before = (k-2)/2 (0 for 3x3);
@@ -256,6 +269,7 @@ inline int enc_conv_tc(const EncCtx& c, const EncConvSlot& cs, const EncNormSlot
   }
   p.B = c.N; p.H = Hout; p.W = Wout; p.TH = th; p.TW = tw;
   p.bn = cs.cout_pad; p.n_total = cs.cout;
+  if (swap) { p.swap = 1; p.cout = cs.cout; p.bn = 256; p.n_total = 256; }
   p.mode = EPI_LINEAR; p.out_scale = 1.0f;
   p.bias = reinterpret_cast<const float*>(c.prep + cs.bias);
   p.inv_scale = reinterpret_cast<const float*>(c.prep + cs.scale) + 1;
@@ -271,7 +285,7 @@ inline int enc_conv_tc(const EncCtx& c, const EncConvSlot& cs, const EncNormSlot
     p.residual = skip; p.res_stride = cs.cout; p.res_c0 = 0;
   } else {
     p.act = ACT_NONE; p.out_hi = nullptr; p.out_lo = nullptr;
-    if (enc_fused_stats() && cs.cout % 32 == 0) {     // statistics partials from this convolution's epilogue
+    if (enc_fused_stats() && (swap || cs.cout % 32 == 0)) {   // statistics partials from this convolution's epilogue
       p.stats_part = c.W.part_tiles;
       p.stats_per_image = c.per_image ? 1 : 0;
       const int tiles = ceil_div(Hout, th) * ceil_div(Wout, tw);

@@ -44,9 +44,9 @@ inline int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uin
   return r == CUDA_SUCCESS ? 0 : RAFT_ERR_DRIVER;
 }
 
-// Measured on B200 (tools/tma_probe.cu): TMA delivery per SM is bound by the NUMBER of boxes (~616 cycles per box,
-// 16 KB or 32 KB alike, not improved by more boxes in flight).  The hi and lo planes of every operand are therefore
-// fetched by ONE box: the plane index is an extra tensor dimension whose stride is (lo - hi) bytes.
+// Measured on B200 (tools/tma_probe.cu, timelines in profiles/): one TMA box costs about max(616 cycles, bytes / 53 B/clk)
+// and an SM serves its boxes one after another, whatever their number in flight.  The hi and lo planes of every operand
+// are therefore fetched by ONE box: the plane index is an extra tensor dimension whose stride is (lo - hi) bytes.
 // Activation planes: rank-5 map (C, W, H, B, plane), box {64, tw*s, th*s, 1, 2} -> smem [hi 128 rows | lo 128 rows].
 inline int make_tmap_act2(CUtensorMap* out, const __half* hi, const __half* lo, int B, int H, int W, int cstride, int tw,
                           int th, int stride = 1) {

@@ -260,8 +260,8 @@ def run_ours(args):
         corr_bytes = B_PER_GPU * (CORR_BYTES_PER_PAIR + ITERS * LOOKUP_BYTES_PER_PAIR_ITER)
         ach_gbs = corr_bytes / (t_corr + ITERS * t_lookup) / 1e9
 
-        if args.quick:
-            parity, max_abs, cpu_pps, cores = {'skipped': '--quick'}, None, None, 0
+        if args.quick or world > 1:     # the CPU legs (oracle parity, CPU baseline) belong to the N=1 line only
+            parity, max_abs, cpu_pps, cores = {'skipped': '--quick' if args.quick else 'reported at N=1'}, None, None, 0
         else:
             log('parity check of the timed configuration against the oracle')
             # --- parity of the timed configuration against the oracle (one pair of batch 0) ---

@@ -387,7 +387,12 @@ static int lookup_launch(const float* const pyr[], const float* coords, int B, i
   p.out_hi = out_hi; p.out_lo = out_lo; p.h_stride = h_stride; p.h_pad = h_pad;
   p.nq = B * h * w; p.levels = levels; p.radius = radius;
   const size_t nwork = (size_t)p.nq * levels;
-  corr_lookup_kernel<<<grid_for(nwork * 32, 256, kNumSMs * 32), 256, 0, st>>>(p);
+  static const int v2 = [] { const char* e = getenv("RAFT_B200_LOOKUP_V2"); return e ? atoi(e) : 0; }();
+  if (v2 && levels == 4 && (radius == 4 || radius == 3) && nwork < (1u << 31)) {   // experiment: compile-time radius / levels
+    if (radius == 4) corr_lookup_fixed_kernel<4, 4><<<grid_for(nwork * 32, 256, kNumSMs * 32), 256, 0, st>>>(p);
+    else corr_lookup_fixed_kernel<3, 4><<<grid_for(nwork * 32, 256, kNumSMs * 32), 256, 0, st>>>(p);
+  } else
+    corr_lookup_kernel<<<grid_for(nwork * 32, 256, kNumSMs * 32), 256, 0, st>>>(p);
   RAFT_COUNT_LAUNCH();
   return raft_launch_status();
 }

@@ -1,23 +1,36 @@
 #!/bin/bash
-# encoder investigation: timelines of encoder convolutions, promotion-group size A/B
+# A/B run of the experiment knobs (scripts/README.md): for each, the relevant GPU parity tests with the knob on, then
+# `bench.py --quick`.  One gpurun call, about 4-5 minutes.  Usage: gpurun --timeout 900 -- 'bash scripts/gpu_ab.sh'
 set -u
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
-for k in 0 1 6; do timeout 120 python tools/timeline_enc.py $k > gpurun_out/timeline_enc$k.log 2>&1; tail -n 16 gpurun_out/timeline_enc$k.log; done
-run() {  # name, env...
+bench() {  # name, env...
   local name=$1; shift
-  env "$@" timeout 300 python bench.py --steps 10 --warmup 3 --quick > gpurun_out/bench_$name.json 2> gpurun_out/bench_$name.err; echo "bench($name) exit $?"
-  python - <<PY
-import json
-d = json.load(open('gpurun_out/bench_$name.json'))
-print('$name', {k: d[k] for k in ('value','ms_per_step')}, 'e2e', d['e2e']['value'])
+  env "$@" timeout 200 python bench.py --steps 10 --warmup 3 --quick > gpurun_out/ab_$name.json 2> gpurun_out/ab_$name.err
+  python - "$name" <<'PY'
+import json, sys
+name = sys.argv[1]
+try:
+    d = json.load(open(f'gpurun_out/ab_{name}.json'))
+    print(f"bench {name:<14} {d['value']:8.1f} pairs/s  {d['ms_per_step']:.3f} ms/step  e2e {d['e2e']['value']:.1f}  corr/lookup ms {d['roofline_corr_lookup']['ms']}")
+except Exception as e:
+    print(f'bench {name}: FAILED ({e})')
 PY
 }
-run default A=1
-run grp3 RAFT_B200_ENC_GROUP=3
-run grp5 RAFT_B200_ENC_GROUP=5
-RAFT_B200_ENC_GROUP=5 timeout 600 python -m pytest tests -m gpu -q -x -p no:cacheprovider -k "encoder or 448" > gpurun_out/t_grp5.log 2>&1
-echo "pytest(grp5) exit $? : $(tail -n 1 gpurun_out/t_grp5.log)"; grep -hE "FAILED|max-abs|assert" gpurun_out/t_grp5.log | head -8
-timeout 600 python -m pytest tests -m gpu -q -x -p no:cacheprovider > gpurun_out/t_all.log 2>&1
-echo "pytest exit $? : $(tail -n 1 gpurun_out/t_all.log)"
+check() {  # name, pytest -k expression, env...
+  local name=$1 k=$2; shift 2
+  env "$@" timeout 600 python -m pytest tests -m gpu -x -q -p no:cacheprovider -k "$k" > gpurun_out/ab_test_$name.log 2>&1
+  echo "tests $name: exit $? : $(tail -n 1 gpurun_out/ab_test_$name.log)"
+}
+bench baseline A=1
+check fused_stats "encoder or reference_test_shape or small_raft" RAFT_B200_FUSED_STATS=1
+bench fused_stats RAFT_B200_FUSED_STATS=1
+check enc_swap "encoder or reference_test_shape or small_raft" RAFT_B200_ENC_SWAP=2
+bench enc_swap RAFT_B200_ENC_SWAP=1
+bench swap_and_stats RAFT_B200_ENC_SWAP=1 RAFT_B200_FUSED_STATS=1
+check pdl "update_block or reference_test_shape or corr_pyramid" RAFT_B200_PDL=1
+bench pdl RAFT_B200_PDL=1
+check lookup_v2 "lookup or reference_test_shape or small_raft" RAFT_B200_LOOKUP_V2=1
+bench lookup_v2 RAFT_B200_LOOKUP_V2=1
+bench all RAFT_B200_ENC_SWAP=1 RAFT_B200_FUSED_STATS=1 RAFT_B200_PDL=1 RAFT_B200_LOOKUP_V2=1

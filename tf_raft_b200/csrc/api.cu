@@ -115,6 +115,10 @@ static int corr_build_tc(const float* f1, const float* f2, int B, int h, int w, 
     }
     p.out_f32 = pyr[l]; p.f32_stride = N2; p.f32_c0 = 0;
     p.out_scale = 1.0f;
+    {   // experiment: TMA stores of the pyramid (needs a 16-byte row stride, i.e. N2 % 4 == 0)
+      static const int tma_store = [] { const char* e = getenv("RAFT_B200_CORR_TMA_STORE"); return e ? atoi(e) : 0; }();
+      if (tma_store && N2 % 4 == 0 && make_tmap_corr_out(&p.out_map, pyr[l], B, N, N2) == 0) p.out_tma = 1;
+    }
     RAFT_COUNT_LAUNCH();
     RAFT_TRY(tc_launch(p, ceil_div(N2, bn), st));
   }

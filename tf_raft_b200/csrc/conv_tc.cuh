@@ -87,6 +87,11 @@ struct alignas(64) TcConvParams {
   // attribute, so this grid's CTAs may be scheduled -- and run their prologue -- while the previous kernel in the stream
   // drains; every thread then executes griddepcontrol.wait before touching global memory.
   int pdl;
+  // kTmaStore instantiation of the correlation (RAFT_B200_CORR_TMA_STORE=1, experiment): each warp's transposed 32 x 32
+  // block leaves shared memory through one TMA store of `out_map` (3-D: target pixel, query pixel, batch; 128-byte swizzle)
+  // instead of 8 x 512-byte store instructions; rows / columns past the level's extent are clipped by the TMA unit.
+  int out_tma;
+  CUtensorMap out_map;
 };
 
 #if defined(__CUDA_ARCH__)
@@ -399,7 +404,7 @@ __device__ __noinline__ void tc_store_corr_block(const float* patch, long long p
 
 // kCorr selects the correlation epilogue at compile time so that its transposition path costs the convolution
 // instantiation neither registers nor code.
-template <bool kCorr, int kEpiWarps, bool kRowEpi, bool kStats = false, bool kSwap = false>
+template <bool kCorr, int kEpiWarps, bool kRowEpi, bool kStats = false, bool kSwap = false, bool kTmaStore = false>
 __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_tc_kernel(const __grid_constant__ TcConvParams p) {
 #if defined(__CUDA_ARCH__)
   // Persistent: CTA c processes output tiles c, c + gridDim.x, ...  A tile is (pixel tile, column tile).  All
@@ -417,7 +422,8 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_tc_kernel(const _
   uint64_t* acc_empty = acc_full + 2;        // [2] promotion warps -> issuer
   uint64_t* b_full = acc_empty + 2;          // resident weights landed
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(b_full + 1);
-  float* patches = reinterpret_cast<float*>(stages + (size_t)nst * p.stage_bytes + 256);   // transposition patches (if any)
+  float* patches = reinterpret_cast<float*>(stages + (size_t)nst * p.stage_bytes + (kTmaStore ? 1024 : 256));   // transposition
+                                             // patches (if any); 1024-byte aligned where a TMA store reads them (swizzle phase)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -624,6 +630,37 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_tc_kernel(const _
           // with 16 bytes each (measured ~20 us per 128 KB tile).  Transpose each 32x32 block through a swizzled smem
           // patch instead: 8 lanes x 16 bytes cover one row, a warp writes 4 full 128-byte rows per instruction.
           float* patch = patches + (warp - 2) * 1024;
+          if constexpr (kTmaStore) {
+#pragma unroll
+            for (int ci = 0; ci < kMaxCh; ++ci) {
+              if (ci < my_chunks) {
+                const int c0 = (chunk0 + ci) * 32;
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // patch no longer being read
+                __syncwarp();
+#pragma unroll
+                for (int qq = 0; qq < 8; ++qq) {
+                  float4 a4 = make_float4(racc[ci][4 * qq], racc[ci][4 * qq + 1], racc[ci][4 * qq + 2], racc[ci][4 * qq + 3]);
+                  if (p.corr_mul != 0.0f) {
+                    a4.x *= p.corr_mul; a4.y *= p.corr_mul; a4.z *= p.corr_mul; a4.w *= p.corr_mul;
+                  } else {
+                    a4.x = __fdiv_rn(a4.x, p.corr_div); a4.y = __fdiv_rn(a4.y, p.corr_div);
+                    a4.z = __fdiv_rn(a4.z, p.corr_div); a4.w = __fdiv_rn(a4.w, p.corr_div);
+                  }
+                  *reinterpret_cast<float4*>(patch + lane * 32 + ((qq ^ (lane & 7)) << 2)) = a4;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the TMA unit
+                __syncwarp();
+                const int col0 = nt * p.bn + c0, row0 = tx * p.TW + quarter * 32;
+                if (lane == 0 && col0 < p.n_total && row0 < p.W) {
+                  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                                   reinterpret_cast<uint64_t>(&p.out_map)),
+                               "r"(smem_u32(patch)), "r"(col0), "r"(row0), "r"(b)
+                               : "memory");
+                  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+              }
+            }
+          } else {
           const long long pix_lane = (x < p.W && y < p.H) ? ((long long)b * p.H + y) * p.W + x : -1;
 #pragma unroll
           for (int ci = 0; ci < kMaxCh; ++ci) {
@@ -638,6 +675,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_tc_kernel(const _
               tc_store_corr_block(patch, pix_lane, p.out_f32, p.f32_stride, nt * p.bn + c0, p.bn - c0, p.n_total, p.corr_mul,
                                   p.corr_div);
             }
+          }
           }
         } else if constexpr (kSwap) {      // operands exchanged: this thread = output channel m, columns = 256 pixels
           const int ch = m;
@@ -786,6 +824,9 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_tc_kernel(const _
     }
   }
 
+  if constexpr (kTmaStore) {
+    if (warp >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // this thread's bulk stores are complete
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
@@ -836,14 +877,14 @@ inline int tc_finalize(TcConvParams& p) {
   if (p.b_stationary) p.stage_bytes = 2 * kABytes;       // weights live in the resident region, stages carry activations only
   else p.b_region_bytes = 0;
   const int patch = tc_uses_patch(p.mode) ? kEpiPatchBytes : 0;   // 8 x 4 KB (correlation) or 16 x 2 KB (GRU q) patches
-  int nst = (kSmemBudget - patch - p.b_region_bytes) / p.stage_bytes;
+  int nst = (kSmemBudget - patch - p.b_region_bytes - (p.out_tma ? 768 : 0)) / p.stage_bytes;
   if (nst > 8) nst = 8;
   p.nstages = nst;
   int cols = 32;
   while (cols < 2 * p.bn) cols <<= 1;           // two accumulator buffers (ping-pong promotion)
   p.tmem_cols = cols;
   if (p.group_chunks <= 0) p.group_chunks = 2;
-  return p.b_region_bytes + nst * p.stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + patch;
+  return p.b_region_bytes + nst * p.stage_bytes + 1024 /*align slack*/ + (p.out_tma ? 1024 : 256) /*barriers*/ + patch;
 }
 
 // Resident-weights plan for a stride-any LINEAR convolution whose whole weight set fits beside >= 2 activation stages
@@ -886,6 +927,7 @@ inline int tc_launch(TcConvParams& p, int n_tiles_n, cudaStream_t stream) {
     RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<false, 16, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<false, 16, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<true, kEpiWarpsCorr, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<true, kEpiWarpsCorr, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   const int mtiles = p.B * p.tiles_y * p.tiles_x;
@@ -899,14 +941,16 @@ inline int tc_launch(TcConvParams& p, int n_tiles_n, cudaStream_t stream) {
     return RAFT_ERR_UNSUPPORTED;
   const int threads = 64 + 32 * (p.mode == EPI_CORR ? kEpiWarpsCorr : kEpiWarpsConv);
   if (!p.pdl) {
-    if (p.mode == EPI_CORR) conv_tc_kernel<true, kEpiWarpsCorr, false><<<grid, threads, smem, stream>>>(p);
+    if (p.mode == EPI_CORR && p.out_tma) conv_tc_kernel<true, kEpiWarpsCorr, false, false, false, true><<<grid, threads, smem, stream>>>(p);
+    else if (p.mode == EPI_CORR) conv_tc_kernel<true, kEpiWarpsCorr, false><<<grid, threads, smem, stream>>>(p);
     else if (p.mode == EPI_GRU_Q) conv_tc_kernel<false, kEpiWarpsConv, false><<<grid, threads, smem, stream>>>(p);
     else if (p.swap) conv_tc_kernel<false, kEpiWarpsConv, true, false, true><<<grid, threads, smem, stream>>>(p);
     else if (p.stats_part) conv_tc_kernel<false, kEpiWarpsConv, true, true><<<grid, threads, smem, stream>>>(p);
     else conv_tc_kernel<false, kEpiWarpsConv, true><<<grid, threads, smem, stream>>>(p);
   } else {                                           // experiment: same kernels with the programmatic-serialization attribute
     void (*kern)(TcConvParams) = conv_tc_kernel<false, kEpiWarpsConv, true>;
-    if (p.mode == EPI_CORR) kern = conv_tc_kernel<true, kEpiWarpsCorr, false>;
+    if (p.mode == EPI_CORR && p.out_tma) kern = conv_tc_kernel<true, kEpiWarpsCorr, false, false, false, true>;
+    else if (p.mode == EPI_CORR) kern = conv_tc_kernel<true, kEpiWarpsCorr, false>;
     else if (p.mode == EPI_GRU_Q) kern = conv_tc_kernel<false, kEpiWarpsConv, false>;
     else if (p.swap) kern = conv_tc_kernel<false, kEpiWarpsConv, true, false, true>;
     else if (p.stats_part) kern = conv_tc_kernel<false, kEpiWarpsConv, true, true>;

@@ -463,9 +463,10 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_tc_kernel(const _
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
-  if (p.pdl) {
+  if (p.pdl && warp != 0) {
     // barriers, TMEM and tensor-map prefetch above touch no global data; from here on the previous grid's results are
     // read (and its inputs overwritten), so wait for it, then let the next grid in the stream start its own prologue.
+    // (Warp 0 = the producer thread waits further down, after it has started fetching the weights of the first stages.)
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   }
@@ -474,6 +475,23 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_tc_kernel(const _
     // ===================== TMA producer =====================
     if (elect_one()) {
       int it = 0;
+      int npre = 0;                // stages whose weight box was issued before the dependency wait (PDL only)
+      if (p.pdl) {
+        // Convolution weights do not depend on the previous grid: fetch them for the first stages of this CTA's first
+        // tile while that grid is still draining, then wait, then fetch the activations.
+        if (!kSwap && !p.b_stationary && p.b_batch_stride == 0 && (int)blockIdx.x < ntiles) {
+          const int n0 = ((int)blockIdx.x / mtiles) * p.bn;
+          npre = min(nst, total);
+#pragma unroll 1
+          for (int i = 0; i < npre; ++i) {
+            mbar_arrive_expect_tx(&full_bar[i], (uint32_t)p.stage_bytes);
+            tma_load_4d(stages + (size_t)i * p.stage_bytes + 2 * kABytes, &p.b_map, &full_bar[i], (i % chunks_per_tap) * kChunkK,
+                        n0, i / chunks_per_tap, 0);
+          }
+        }
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+      }
       if (p.b_stationary) {
         // Measured (tools/tma_probe.cu, timelines): a TMA box costs max(~616 cycles, bytes / 53 B/clk) and boxes are
         // served one after the other, so for narrow layers (cout 64: a 16 KB weight box per chunk) the weight box
@@ -502,7 +520,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_tc_kernel(const _
               mbar_wait(&empty_bar[s], phase ^ 1u);
               if (p.dbg && blockIdx.x == 0 && it < 512) p.dbg[it] = clock64();              // slot free
               uint8_t* st = stages + (size_t)s * p.stage_bytes;
-              mbar_arrive_expect_tx(&full_bar[s], (uint32_t)p.stage_bytes);
+              if (it >= npre) mbar_arrive_expect_tx(&full_bar[s], (uint32_t)p.stage_bytes);
               const int c = p.seg_c0[seg] + ch * kChunkK;
               // two boxes per stage: [A_hi | A_lo] and [B_hi | B_lo] (TMA cost is per box, not per byte)
               if constexpr (kSwap) {   // weights -> M-operand slot (128 rows x 2 planes), 256 pixels -> N-operand slot
@@ -510,7 +528,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_tc_kernel(const _
                 tma_load_5d(st + 2 * kABytes, &p.a_map[seg], &full_bar[s], c, x0 + dx, y0 + dy, b, 0);
               } else {
                 tma_load_5d(st, &p.a_map[seg], &full_bar[s], c, x0 + dx, y0 + dy, b, 0);
-                if (!p.b_stationary) tma_load_4d(st + 2 * kABytes, &p.b_map, &full_bar[s], kc * kChunkK, n0, tcoord, 0);
+                if (!p.b_stationary && it >= npre) tma_load_4d(st + 2 * kABytes, &p.b_map, &full_bar[s], kc * kChunkK, n0, tcoord, 0);
               }
             }
           }
@@ -924,11 +942,17 @@ inline int tc_launch(TcConvParams& p, int n_tiles_n, cudaStream_t stream) {
   if (!attr_set) {
     RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<false, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<false, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<false, 16, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<false, 16, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<true, kEpiWarpsCorr, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<true, kEpiWarpsCorr, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
+  }
+  if (p.stats_part || p.swap || p.out_tma) {       // experiment instantiations: configured only when one is selected
+    static bool attr_set_x = false;
+    if (!attr_set_x) {
+      RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<false, 16, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<false, 16, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<true, kEpiWarpsCorr, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr_set_x = true;
+    }
   }
   const int mtiles = p.B * p.tiles_y * p.tiles_x;
   p.n_tiles_n = n_tiles_n;

@@ -208,6 +208,25 @@ static int gru_tc(const UpdateCtx& c, float* h, int lzr, int lq, int hid, int x_
   return 0;
 }
 
+// flow_head.conv2 on CUDA cores from the fp16 operand planes (experiment, see flow_head2_kernel); returns false when
+// the knob is off and the caller should run the tensor-core layer.
+static bool fh2_simt(const UpdateCtx& c, int conv_idx, const __half* hi, const __half* lo, int cstride, int C, float* delta,
+                     int* status) {
+  static const int on = [] { const char* e = getenv("RAFT_B200_FH2_SIMT"); return e ? atoi(e) : 0; }();
+  if (!on || C % 32 != 0) return false;
+  FlowHead2Params q;
+  memset(&q, 0, sizeof(q));
+  q.hi = hi; q.lo = lo; q.cstride = cstride; q.c0 = 0; q.C = C;
+  q.w = reinterpret_cast<const float*>(c.prepared + c.PL.raw_w[conv_idx]);
+  q.bias = reinterpret_cast<const float*>(c.prepared + c.PL.raw_b[conv_idx]);
+  q.delta = delta; q.B = c.B; q.H = c.h; q.W = c.w;
+  const int tiles = c.B * ceil_div(c.h, 8) * ceil_div(c.w, 16);
+  flow_head2_kernel<<<tiles, 128, 0, c.stream>>>(q);
+  RAFT_COUNT_LAUNCH();
+  *status = raft_launch_status();
+  return true;
+}
+
 static int update_core_tc(const UpdateCtx& c, float* h, float* delta, float* mask) {
   const Workspace& W = c.W;
   const VariantDims d = variant_dims(c.variant);
@@ -255,7 +274,10 @@ static int update_core_tc(const UpdateCtx& c, float* h, float* delta, float* mas
       TcSeg s[1] = {{W.h_hi, W.h_lo, d.s_h, 0, 2}};
       RAFT_TRY(launch_tc_layer(c, 8, 1, s, p, mask ? 2 : 1));
     }
-    {  // flow_head.conv2 3x3 256->2
+    int fh2_status = 0;
+    if (fh2_simt(c, BFH2, W.fm_hi, W.fm_lo, d.s_fm, 256, delta, &fh2_status)) {
+      RAFT_TRY(fh2_status);
+    } else {  // flow_head.conv2 3x3 256->2
       tc_params_init(p, EPI_LINEAR, ACT_NONE, 2);
       p.out_f32 = delta; p.f32_stride = 2;
       TcSeg s[1] = {{W.fm_hi, W.fm_lo, d.s_fm, 0, 4}};
@@ -303,7 +325,10 @@ static int update_core_tc(const UpdateCtx& c, float* h, float* delta, float* mas
       TcSeg s[1] = {{W.h_hi, W.h_lo, d.s_h, 0, 2}};
       RAFT_TRY(launch_tc_layer(c, 5, 1, s, p));
     }
-    {  // flow_head.conv2 3x3 128->2
+    int fh2_status = 0;
+    if (fh2_simt(c, SFH2, W.fm_hi, W.fm_lo, d.s_fm, 128, delta, &fh2_status)) {
+      RAFT_TRY(fh2_status);
+    } else {  // flow_head.conv2 3x3 128->2
       tc_params_init(p, EPI_LINEAR, ACT_NONE, 2);
       p.out_f32 = delta; p.f32_stride = 2;
       TcSeg s[1] = {{W.fm_hi, W.fm_lo, d.s_fm, 0, 2}};

@@ -35,6 +35,8 @@ check lookup_v2 "lookup or reference_test_shape or small_raft" RAFT_B200_LOOKUP_
 bench lookup_v2 RAFT_B200_LOOKUP_V2=1
 check fh2_simt "update_block or reference_test_shape or small_raft" RAFT_B200_FH2_SIMT=1
 bench fh2_simt RAFT_B200_FH2_SIMT=1
+check two_streams "reference_test_shape or model_api or other_resolutions" RAFT_B200_TWO_STREAMS=1
+bench two_streams RAFT_B200_TWO_STREAMS=1
 check corr_tma "corr or pyramid or reference_test_shape or small_raft" RAFT_B200_CORR_TMA_STORE=1
 bench corr_tma RAFT_B200_CORR_TMA_STORE=1
-bench all RAFT_B200_FH2_SIMT=1 RAFT_B200_CORR_TMA_STORE=1 RAFT_B200_ENC_SWAP=1 RAFT_B200_FUSED_STATS=1 RAFT_B200_PDL=1 RAFT_B200_LOOKUP_V2=1
+bench all RAFT_B200_TWO_STREAMS=1 RAFT_B200_FH2_SIMT=1 RAFT_B200_CORR_TMA_STORE=1 RAFT_B200_ENC_SWAP=1 RAFT_B200_FUSED_STATS=1 RAFT_B200_PDL=1 RAFT_B200_LOOKUP_V2=1

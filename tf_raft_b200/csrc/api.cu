@@ -208,6 +208,47 @@ static int gru_tc(const UpdateCtx& c, float* h, int lzr, int lq, int hid, int x_
   return 0;
 }
 
+// Side stream of the two-stream experiment (RAFT_B200_TWO_STREAMS=1): the flow branch of the motion encoder runs beside
+// the lookup + correlation branch of the same iteration and joins before `conv`.  Created once, on first use.
+struct SideStream { cudaStream_t s; cudaEvent_t fork, join; bool ok; };
+static SideStream& side_stream() {
+  static SideStream S = [] {
+    SideStream t;
+    memset(&t, 0, sizeof(t));
+    const char* e = getenv("RAFT_B200_TWO_STREAMS");
+    if (e && atoi(e) && cudaStreamCreateWithFlags(&t.s, cudaStreamNonBlocking) == cudaSuccess &&
+        cudaEventCreateWithFlags(&t.fork, cudaEventDisableTiming) == cudaSuccess &&
+        cudaEventCreateWithFlags(&t.join, cudaEventDisableTiming) == cudaSuccess)
+      t.ok = true;
+    return t;
+  }();
+  return S;
+}
+
+// Flow branch of BasicMotionEncoder (update.py:98-99): convf1 7x7 2->128 + relu, convf2 3x3 128->64 + relu ->
+// cor_flo[192:256).  Depends only on the current flow, so it may run beside the lookup and the correlation branch.
+static int flow_branch_basic_tc(const UpdateCtx& c) {
+  const Workspace& W = c.W;
+  const VariantDims d = variant_dims(c.variant);
+  TcConvParams p;
+  {  // convf1 7x7 2->128 + relu: K = 98 -> gather the window into 128-channel planes, run as a 1x1 GEMM
+    const size_t npix = (size_t)c.B * c.h * c.w;
+    flow_im2col_kernel<<<grid_for(npix * 128), 256, 0, c.stream>>>(W.flow, c.B, c.h, c.w, W.fim_hi, W.fim_lo);
+    RAFT_COUNT_LAUNCH();
+    tc_params_init(p, EPI_LINEAR, ACT_RELU, 128);
+    p.out_hi = W.flo1_hi; p.out_lo = W.flo1_lo; p.h_stride = d.s_flo1;
+    TcSeg s[1] = {{W.fim_hi, W.fim_lo, 128, 0, 2}};
+    RAFT_TRY(launch_tc_layer(c, 11, 1, s, p));
+  }
+  {  // convf2 3x3 128->64 + relu -> cor_flo[192:256)
+    tc_params_init(p, EPI_LINEAR, ACT_RELU, 64);
+    p.out_hi = W.cf_hi; p.out_lo = W.cf_lo; p.h_stride = d.s_cf; p.h_c0 = 192;
+    TcSeg s[1] = {{W.flo1_hi, W.flo1_lo, d.s_flo1, 0, 2}};
+    RAFT_TRY(launch_tc_layer(c, 2, 1, s, p));
+  }
+  return 0;
+}
+
 // flow_head.conv2 on CUDA cores from the fp16 operand planes (experiment, see flow_head2_kernel); returns false when
 // the knob is off and the caller should run the tensor-core layer.
 static bool fh2_simt(const UpdateCtx& c, int conv_idx, const __half* hi, const __half* lo, int cstride, int C, float* delta,
@@ -227,7 +268,8 @@ static bool fh2_simt(const UpdateCtx& c, int conv_idx, const __half* hi, const _
   return true;
 }
 
-static int update_core_tc(const UpdateCtx& c, float* h, float* delta, float* mask) {
+static int update_core_tc(const UpdateCtx& c, float* h, float* delta, float* mask, bool flow_done = false,
+                          cudaEvent_t flow_join = nullptr) {
   const Workspace& W = c.W;
   const VariantDims d = variant_dims(c.variant);
   TcConvParams p;
@@ -244,21 +286,8 @@ static int update_core_tc(const UpdateCtx& c, float* h, float* delta, float* mas
       TcSeg s[1] = {{W.cor1_hi, W.cor1_lo, d.s_cor1, 0, 4}};
       RAFT_TRY(launch_tc_layer(c, 1, 1, s, p));
     }
-    {  // convf1 7x7 2->128 + relu: K = 98 -> gather the window into 128-channel planes, run as a 1x1 GEMM
-      const size_t npix = (size_t)c.B * c.h * c.w;
-      flow_im2col_kernel<<<grid_for(npix * 128), 256, 0, c.stream>>>(W.flow, c.B, c.h, c.w, W.fim_hi, W.fim_lo);
-      RAFT_COUNT_LAUNCH();
-      tc_params_init(p, EPI_LINEAR, ACT_RELU, 128);
-      p.out_hi = W.flo1_hi; p.out_lo = W.flo1_lo; p.h_stride = d.s_flo1;
-      TcSeg s[1] = {{W.fim_hi, W.fim_lo, 128, 0, 2}};
-      RAFT_TRY(launch_tc_layer(c, 11, 1, s, p));
-    }
-    {  // convf2 3x3 128->64 + relu -> cor_flo[192:256)
-      tc_params_init(p, EPI_LINEAR, ACT_RELU, 64);
-      p.out_hi = W.cf_hi; p.out_lo = W.cf_lo; p.h_stride = d.s_cf; p.h_c0 = 192;
-      TcSeg s[1] = {{W.flo1_hi, W.flo1_lo, d.s_flo1, 0, 2}};
-      RAFT_TRY(launch_tc_layer(c, 2, 1, s, p));
-    }
+    if (!flow_done) RAFT_TRY(flow_branch_basic_tc(c));      // convf1, convf2 (update.py:98-99)
+    else RAFT_CUDA_TRY(cudaStreamWaitEvent(c.stream, flow_join, 0));   // ... already running on the side stream
     {  // conv 3x3 256->126 + relu, concat flow -> x[128:256)
       tc_params_init(p, EPI_LINEAR, ACT_RELU, 126);
       p.out_hi = W.x_hi; p.out_lo = W.x_lo; p.h_stride = d.s_x; p.h_c0 = 128;
@@ -730,9 +759,19 @@ int raft_b200_forward_loop(int variant, const void* prepared, const float* const
   for (int i = 0; i < iters; ++i) {
     float* mask = (variant == RAFT_VARIANT_BASIC && flow_up[i]) ? W.mask : nullptr;
     if (precision == RAFT_PREC_F16X2) {
+      SideStream& S = side_stream();
+      const bool fork = S.ok && variant == RAFT_VARIANT_BASIC;
+      if (fork) {   // experiment: flow branch on the side stream, beside the lookup and the correlation branch
+        RAFT_CUDA_TRY(cudaEventRecord(S.fork, c.stream));
+        RAFT_CUDA_TRY(cudaStreamWaitEvent(S.s, S.fork, 0));
+        UpdateCtx c2 = c;
+        c2.stream = S.s;
+        RAFT_TRY(flow_branch_basic_tc(c2));
+        RAFT_CUDA_TRY(cudaEventRecord(S.join, S.s));
+      }
       RAFT_TRY(lookup_launch(pyr, coords1, B, h, w, levels, radius, nullptr, 0, W.corr_hi, W.corr_lo, d.s_corr, d.s_corr,
                              c.stream));                                                            // model.py:95
-      RAFT_TRY(update_core_tc(c, net, W.delta, mask));                                              // :99
+      RAFT_TRY(update_core_tc(c, net, W.delta, mask, fork, S.join));                                // :99
     } else {
       RAFT_TRY(lookup_launch(pyr, coords1, B, h, w, levels, radius, W.corr, d.corr_ch, nullptr, nullptr, 0, 0, c.stream));
       RAFT_TRY(update_core_fp32(c, net, W.delta, mask));

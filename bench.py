@@ -21,7 +21,6 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
-import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 H, W, ITERS, B_PER_GPU = 448, 512, 12, 4

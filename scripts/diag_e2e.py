@@ -2,7 +2,7 @@
 import os, sys
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), '..'))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
-import numpy as np, torch
+import torch
 import cases
 from oracle import raft_torch as rt, weights
 import tf_raft_b200 as T

@@ -2,7 +2,6 @@
 answers, and the committed golden vectors are what the oracle produces today.  CPU only."""
 import numpy as np
 import torch
-import torch.nn.functional as F
 
 import cases
 from oracle import corr_np, raft_torch as rt, tf_ops, weights

@@ -6,11 +6,9 @@
 upsample) is ONE call into libraft_b200.so (raft_b200_forward_loop); the correlation pyramid is
 another (raft_b200_corr_pyramid_build).  Optionally the loop is replayed from a CUDA graph.
 """
-import ctypes
 from collections import OrderedDict
 
 import torch
-import torch.nn.functional as F
 
 from . import _lib
 from .layers.corr import CorrBlock, coords_grid, upflow8

@@ -22,6 +22,7 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv
 timeout 300 ncu --set full --clock-control none -k regex:corr_lookup_kernel -s 14 -c 1 -o gpurun_out/prof_r01_lookup python scripts/profile_loop.py f16x2 2 > gpurun_out/ncu_full2.log 2>&1; echo "ncu lookup exit $?"
 python tools/timeline.py 4 > gpurun_out/timeline_zr1.log 2>&1
 [ -z "${FAST:-}" ] && ./tools/tma_probe > gpurun_out/tma_probe.log 2>&1
+[ -z "${FAST:-}" ] && timeout 300 python tools/corr_sweep.py > gpurun_out/corr_sweep.log 2>&1
 for l in 0 5 8; do python tools/timeline.py $l 2>&1 | tail -n 1 >> gpurun_out/timeline_zr1.log; done
 python tools/timeline_enc.py 1 > gpurun_out/timeline_enc1.log 2>&1
 RAFT_B200_ENC_GROUP=2 timeout 200 python bench.py --steps 10 --warmup 3 --quick > gpurun_out/bench_r01_encgroup2.json 2> /dev/null; echo "bench encgroup2 exit $?"

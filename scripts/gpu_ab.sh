@@ -39,4 +39,5 @@ check two_streams "reference_test_shape or model_api or other_resolutions" RAFT_
 bench two_streams RAFT_B200_TWO_STREAMS=1
 check corr_tma "corr or pyramid or reference_test_shape or small_raft" RAFT_B200_CORR_TMA_STORE=1
 bench corr_tma RAFT_B200_CORR_TMA_STORE=1
+timeout 200 python bench.py --steps 10 --warmup 3 --quick --pipeline > gpurun_out/ab_pipeline.json 2> gpurun_out/ab_pipeline.err; python -c "import json; d=json.load(open('gpurun_out/ab_pipeline.json')); print('bench pipeline e2e', d['e2e'])"
 bench all RAFT_B200_TWO_STREAMS=1 RAFT_B200_FH2_SIMT=1 RAFT_B200_CORR_TMA_STORE=1 RAFT_B200_ENC_SWAP=1 RAFT_B200_FUSED_STATS=1 RAFT_B200_PDL=1 RAFT_B200_LOOKUP_V2=1

@@ -62,3 +62,25 @@ def test_predict_sharded_world2_gloo(batch):
         assert p.exitcode == 0
     assert [r[1] for r in res] == [True, True]
     assert [r[2] for r in res] == [2.0, 2.0]          # max over ranks of (1 + rank)
+
+
+def test_predict_stream_schedule_on_cpu():
+    """Plumbing of the pipelined predict (parallel.predict_stream): order, one result per pair, look-ahead of one."""
+    import torch
+    from tf_raft_b200 import parallel
+    calls = []
+
+    def batches():
+        for i in range(5):
+            calls.append(('fetch', i))
+            yield torch.full((2, 4, 4, 3), float(i)), torch.full((2, 4, 4, 3), float(10 * i))
+
+    def predict(a, b):
+        calls.append(('predict', int(a[0, 0, 0, 0])))
+        return a[..., :2] + b[..., :2]
+
+    outs = list(parallel.predict_stream(predict, batches(), 'cpu'))
+    assert [float(o[0, 0, 0, 0]) for o in outs] == [0.0, 11.0, 22.0, 33.0, 44.0]
+    # pair i+1 is fetched (uploaded) before pair i is computed
+    assert calls[:4] == [('fetch', 0), ('fetch', 1), ('predict', 0), ('fetch', 2)]
+    assert list(parallel.predict_stream(predict, iter(()), 'cpu')) == []

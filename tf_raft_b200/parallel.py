@@ -57,3 +57,58 @@ def max_over_ranks(value, device, group=None):
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return float(t.item())
+
+
+def predict_stream(predict_fn, batches, device):
+    """Pipelined inference over host batches: yields `predict_fn(image1, image2)` for every `(image1, image2)` pair of
+    `batches` as host tensors, in order.
+
+    On a CUDA device the upload of pair i+1 is issued on a copy stream while pair i computes on the current stream, and
+    the result of pair i is read back asynchronously into pinned memory while pair i+1 computes; pass pinned host
+    tensors for the uploads to be asynchronous.  Every pair still makes the full host -> device -> host round trip; only
+    the waiting is overlapped.  (`device` of type 'cpu' runs the same schedule synchronously: plumbing tests.)"""
+    device = torch.device(device)
+    cuda = device.type == 'cuda'
+    main = torch.cuda.current_stream(device) if cuda else None
+    copy = torch.cuda.Stream(device=device) if cuda else None
+
+    def upload(pair):
+        if not cuda:
+            return pair[0], pair[1], None
+        with torch.cuda.stream(copy):
+            a = pair[0].to(device, non_blocking=True)
+            b = pair[1].to(device, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(copy)
+        return a, b, ready
+
+    it = iter(batches)
+    first = next(it, None)
+    if first is None:
+        return
+    cur, pending = upload(first), None
+    while cur is not None:
+        nxt_pair = next(it, None)
+        nxt = upload(nxt_pair) if nxt_pair is not None else None     # overlaps the compute issued below
+        a, b, ready = cur
+        if cuda:
+            main.wait_event(ready)
+            a.record_stream(main)                                     # allocated under the copy stream, consumed here
+            b.record_stream(main)
+        out = predict_fn(a, b)
+        if cuda:
+            host_out = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+            host_out.copy_(out, non_blocking=True)                    # stream-ordered after the compute, before the next one
+            done = torch.cuda.Event()
+            done.record(main)
+        else:
+            host_out, done = out, None
+        if pending is not None:
+            if pending[1] is not None:
+                pending[1].synchronize()
+            yield pending[0]
+        pending = (host_out, done)
+        cur = nxt
+    if pending[1] is not None:
+        pending[1].synchronize()
+    yield pending[0]

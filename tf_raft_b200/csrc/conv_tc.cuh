@@ -938,20 +938,25 @@ inline int tc_launch(TcConvParams& p, int n_tiles_n, cudaStream_t stream) {
   if (p.stride < 1) p.stride = 1;
   const int smem = tc_finalize(p);
   if (p.nstages < 2) return RAFT_ERR_UNSUPPORTED;
-  static bool attr_set = false;   // benign race: idempotent
+  // the attribute is per device: one bit per device ordinal (benign race: the calls are idempotent)
+  int dev = 0;
+  RAFT_CUDA_TRY(cudaGetDevice(&dev));
+  const unsigned long long dev_bit = 1ull << (dev & 63);
+  static unsigned long long attr_set_mask = 0;
+  const bool attr_set = (attr_set_mask & dev_bit) != 0;
   if (!attr_set) {
     RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<false, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<false, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<true, kEpiWarpsCorr, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+    attr_set_mask |= dev_bit;
   }
   if (p.stats_part || p.swap || p.out_tma) {       // experiment instantiations: configured only when one is selected
-    static bool attr_set_x = false;
-    if (!attr_set_x) {
+    static unsigned long long attr_set_x_mask = 0;
+    if (!(attr_set_x_mask & dev_bit)) {
       RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<false, 16, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<false, 16, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<true, kEpiWarpsCorr, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      attr_set_x = true;
+      attr_set_x_mask |= dev_bit;
     }
   }
   const int mtiles = p.B * p.tiles_y * p.tiles_x;

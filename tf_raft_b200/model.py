@@ -134,9 +134,12 @@ class RAFT:
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 outs = self._forward(s1, s2, False, last_only)
-            entry = (graph, s1, s2, outs, self._last)
+            # The captured kernels hold raw addresses of the encoder / update-block workspaces; those caches keep one
+            # shape at a time, so the graph entry owns references to the buffers it was captured with.
+            keep = [list(m._ws.values()) for m in (self.fnet, self.cnet, self.update_block)]
+            entry = (graph, s1, s2, outs, self._last, keep)
             self._graphs[key] = entry
-        graph, s1, s2, outs, last = entry
+        graph, s1, s2, outs, last, _keep = entry
         s1.copy_(image1, non_blocking=True)
         s2.copy_(image2, non_blocking=True)
         graph.replay()

@@ -31,8 +31,7 @@ bench enc_swap RAFT_B200_ENC_SWAP=1
 bench swap_and_stats RAFT_B200_ENC_SWAP=1 RAFT_B200_FUSED_STATS=1
 check pdl "update_block or reference_test_shape or corr_pyramid" RAFT_B200_PDL=1
 bench pdl RAFT_B200_PDL=1
-check lookup_v2 "lookup or reference_test_shape or small_raft" RAFT_B200_LOOKUP_V2=1
-bench lookup_v2 RAFT_B200_LOOKUP_V2=1
+bench lookup_gather RAFT_B200_LOOKUP_GATHER=1
 check fh2_simt "update_block or reference_test_shape or small_raft" RAFT_B200_FH2_SIMT=1
 bench fh2_simt RAFT_B200_FH2_SIMT=1
 check two_streams "reference_test_shape or model_api or other_resolutions" RAFT_B200_TWO_STREAMS=1
@@ -40,4 +39,4 @@ bench two_streams RAFT_B200_TWO_STREAMS=1
 check corr_tma "corr or pyramid or reference_test_shape or small_raft" RAFT_B200_CORR_TMA_STORE=1
 bench corr_tma RAFT_B200_CORR_TMA_STORE=1
 timeout 200 python bench.py --steps 10 --warmup 3 --quick --pipeline > gpurun_out/ab_pipeline.json 2> gpurun_out/ab_pipeline.err; python -c "import json; d=json.load(open('gpurun_out/ab_pipeline.json')); print('bench pipeline e2e', d['e2e'])"
-bench all RAFT_B200_TWO_STREAMS=1 RAFT_B200_FH2_SIMT=1 RAFT_B200_CORR_TMA_STORE=1 RAFT_B200_ENC_SWAP=1 RAFT_B200_FUSED_STATS=1 RAFT_B200_PDL=1 RAFT_B200_LOOKUP_V2=1
+bench all RAFT_B200_TWO_STREAMS=1 RAFT_B200_FH2_SIMT=1 RAFT_B200_CORR_TMA_STORE=1 RAFT_B200_ENC_SWAP=1 RAFT_B200_FUSED_STATS=1 RAFT_B200_PDL=1

@@ -1,6 +1,9 @@
 // extern "C" entry points of libraft_b200.so (see include/raft_b200.h for the contract and the
 // reference file:line each one replaces).  Host code only decides shapes and launches kernels;
 // there is no CPU compute path.
+#include <algorithm>
+
+#include "corr_tc.cuh"
 #include "encoder.cuh"
 
 namespace raft {
@@ -68,61 +71,83 @@ static int corr_build_fp32(const float* f1, const float* f2, int B, int h, int w
 // Tensor-core path: level l = fmap1 . avgpool^l(fmap2)^T / sqrt(C).  Pooling is linear, so pooling
 // the 256-channel features (a few MB) before the GEMM equals pooling the N x N volume after it
 // (up to fp32 summation order) and every level is written exactly once, straight from TMEM.
+// Two launches: corr_prep_kernel (pool + hi/lo split of both feature maps) and corr_tc_kernel (all levels).
 static int corr_build_tc(const float* f1, const float* f2, int B, int h, int w, int C, int levels, float* const pyr[],
                          void* ws, cudaStream_t st) {
   if (C % kChunkK != 0) return RAFT_ERR_BAD_SHAPE;
   CorrWs W = corr_ws_layout(ws, B, h, w, C, levels, RAFT_PREC_F16X2);
   const int N = h * w;
   const size_t npix = (size_t)B * N;
-  split_plane_kernel<<<grid_for(npix * C), 256, 0, st>>>(f1, C, 0, C, C, W.f1_hi, W.f1_lo, C, 0, npix, 1.0f);
-  RAFT_COUNT_LAUNCH();
-  int lh = h, lw = w;
-  const float* src = f2;
-  for (int l = 0; l < levels; ++l) {
-    if (l > 0) {
-      const size_t total = (size_t)B * (lh / 2) * (lw / 2) * C;
-      avgpool2x2_kernel<<<grid_for(total), 256, 0, st>>>(src, W.f2_lvl[l], (size_t)B, lh, lw, C);
+  if (levels <= 4) {
+    CorrPrepParams q;
+    memset(&q, 0, sizeof(q));
+    q.f1 = f1; q.f2 = f2; q.f1_hi = W.f1_hi; q.f1_lo = W.f1_lo;
+    for (int l = 0; l < levels; ++l) { q.f2_hi[l] = W.f2_hi[l]; q.f2_lo[l] = W.f2_lo[l]; }
+    q.B = B; q.h = h; q.w = w; q.C = C; q.levels = levels;
+    q.patches_x = ceil_div(w, 8); q.patches_y = ceil_div(h, 8);
+    q.npatch = B * q.patches_x * q.patches_y;
+    const int split_blocks = (int)std::min<size_t>((npix * C / 4 + 127) / 128, (size_t)kNumSMs * 8);
+    corr_prep_kernel<<<q.npatch + split_blocks, 128, 0, st>>>(q);
+    RAFT_COUNT_LAUNCH();
+  } else {                                   // deeper pyramids: generic pooling / split kernels, level by level
+    split_plane_kernel<<<grid_for(npix * C), 256, 0, st>>>(f1, C, 0, C, C, W.f1_hi, W.f1_lo, C, 0, npix, 1.0f);
+    RAFT_COUNT_LAUNCH();
+    int lh = h, lw = w;
+    const float* src = f2;
+    for (int l = 0; l < levels; ++l) {
+      if (l > 0) {
+        const size_t total = (size_t)B * (lh / 2) * (lw / 2) * C;
+        avgpool2x2_kernel<<<grid_for(total), 256, 0, st>>>(src, W.f2_lvl[l], (size_t)B, lh, lw, C);
+        RAFT_COUNT_LAUNCH();
+        src = W.f2_lvl[l];
+        lh /= 2;
+        lw /= 2;
+      }
+      const size_t np2 = (size_t)B * lh * lw;
+      split_plane_kernel<<<grid_for(np2 * C), 256, 0, st>>>(src, C, 0, C, C, W.f2_hi[l], W.f2_lo[l], C, 0, np2, 1.0f);
       RAFT_COUNT_LAUNCH();
-      src = W.f2_lvl[l];
-      lh /= 2;
-      lw /= 2;
     }
-    const size_t np2 = (size_t)B * lh * lw;
-    split_plane_kernel<<<grid_for(np2 * C), 256, 0, st>>>(src, C, 0, C, C, W.f2_hi[l], W.f2_lo[l], C, 0, np2, 1.0f);
-    RAFT_COUNT_LAUNCH();
-    RAFT_TRY(raft_launch_status());
-
-    const int N2 = lh * lw;
-    TcConvParams p;
-    memset(&p, 0, sizeof(p));
-    // A: fmap1 as a (B, 1, N, C) "image" -> 128 consecutive queries per tile
-    RAFT_TRY(make_tmap_act2(&p.a_map[0], W.f1_hi, W.f1_lo, B, 1, N, C, 128, 1));
-    int bn = 256;
-    if (N2 < 256) bn = round_up(N2, 16);
-    // B: level-l features [B][N2][C] -> the batch index rides in the "tap" coordinate
-    RAFT_TRY(make_tmap_wgt2(&p.b_map, W.f2_hi[l], W.f2_lo[l], B, N2, C, bn));
-    p.nseg = 1; p.seg_chunks[0] = C / kChunkK; p.seg_c0[0] = 0;
-    p.kh = p.kw = 1; p.ph = p.pw = 0;
-    p.B = B; p.H = 1; p.W = N; p.TH = 1; p.TW = 128;
-    p.bn = bn; p.n_total = N2;
-    p.b_batch_stride = 1;
-    p.mode = EPI_CORR;
-    p.corr_div = sqrtf((float)C);
-    {
-      int e = 0;
-      const float m = frexpf(p.corr_div, &e);          // sqrt(C) = m * 2^e; m == 0.5 <=> exact power of two
-      p.corr_mul = (m == 0.5f && p.corr_div * p.corr_div == (float)C) ? 1.0f / p.corr_div : 0.0f;
-    }
-    p.out_f32 = pyr[l]; p.f32_stride = N2; p.f32_c0 = 0;
-    p.out_scale = 1.0f;
-    {   // experiment: TMA stores of the pyramid (needs a 16-byte row stride, i.e. N2 % 4 == 0)
-      static const int tma_store = [] { const char* e = getenv("RAFT_B200_CORR_TMA_STORE"); return e ? atoi(e) : 0; }();
-      if (tma_store && N2 % 4 == 0 && make_tmap_corr_out(&p.out_map, pyr[l], B, N, N2) == 0) p.out_tma = 1;
-    }
-    RAFT_COUNT_LAUNCH();
-    RAFT_TRY(tc_launch(p, ceil_div(N2, bn), st));
   }
-  return 0;
+  RAFT_TRY(raft_launch_status());
+
+  CorrTcParams p;
+  memset(&p, 0, sizeof(p));
+  // A: fmap1 as a (B, 1, N, C) "image" -> 128 consecutive queries per tile
+  RAFT_TRY(make_tmap_act2(&p.a_map, W.f1_hi, W.f1_lo, B, 1, N, C, 128, 1));
+  p.levels = levels; p.B = B; p.N = N; p.chunks = C / kChunkK;
+  p.mtiles_img = ceil_div(N, kTileM);
+  const int mtiles = B * p.mtiles_img;
+  int lh = h, lw = w;
+  for (int l = 0; l < levels; ++l) {
+    const int N2 = lh * lw;
+    const int ntn = ceil_div(N2, 256);
+    const int bn = round_up(ceil_div(N2, ntn), 16);
+    // B: level-l features [B][N2][C] -> the batch index rides in the "tap" coordinate
+    RAFT_TRY(make_tmap_wgt2(&p.b_map[l], W.f2_hi[l], W.f2_lo[l], B, N2, C, bn));
+    p.out[l] = pyr[l];
+    p.n2[l] = N2; p.bn[l] = bn;
+    p.tile0[l + 1] = p.tile0[l] + mtiles * ntn;
+    lh /= 2;
+    lw /= 2;
+  }
+  p.corr_div = sqrtf((float)C);
+  {
+    int e = 0;
+    const float m = frexpf(p.corr_div, &e);          // sqrt(C) = m * 2^e; m == 0.5 <=> exact power of two
+    p.corr_mul = (m == 0.5f && p.corr_div * p.corr_div == (float)C) ? 1.0f / p.corr_div : 0.0f;
+  }
+  if (g_dbg_layer == 2000) p.dbg = g_dbg_buf;
+  int dev = 0;
+  RAFT_CUDA_TRY(cudaGetDevice(&dev));
+  static unsigned long long attr_mask = 0;          // per-device attribute (benign race: idempotent)
+  if (!(attr_mask & (1ull << (dev & 63)))) {
+    RAFT_CUDA_TRY(cudaFuncSetAttribute(corr_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCorrSmemBytes));
+    attr_mask |= 1ull << (dev & 63);
+  }
+  const int ntiles = p.tile0[levels];
+  corr_tc_kernel<<<ntiles < kNumSMs ? ntiles : kNumSMs, kCorrThreads, kCorrSmemBytes, st>>>(p);
+  RAFT_COUNT_LAUNCH();
+  return raft_launch_status();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -187,7 +212,10 @@ static void tc_params_init(TcConvParams& p, int mode, int act, int n_total) {
   p.out_scale = 1.0f;
 }
 
-static int gru_tc(const UpdateCtx& c, float* h, int lzr, int lq, int hid, int x_chunks) {
+static TcDeps dep1(int layer, int ntile = -1) { return TcDeps{1, {layer, -1}, {ntile, -1}}; }
+static TcDeps dep2(int l0, int l1) { return TcDeps{2, {l0, l1}, {-1, -1}}; }
+
+static int gru_tc(const UpdateCtx& c, float* h, int lzr, int lq, int hid, int x_chunks, int src_layer) {
   const Workspace& W = c.W;
   const VariantDims d = variant_dims(c.variant);
   TcConvParams p;
@@ -196,33 +224,16 @@ static int gru_tc(const UpdateCtx& c, float* h, int lzr, int lq, int hid, int x_
     p.z = W.z; p.h = h; p.hid = hid;
     p.out_hi = W.rh_hi; p.out_lo = W.rh_lo; p.h_stride = d.s_h; p.h_c0 = 0;
     TcSeg segs[2] = {{W.h_hi, W.h_lo, d.s_h, 0, d.s_h / kChunkK}, {W.x_hi, W.x_lo, d.s_x, 0, x_chunks}};
-    RAFT_TRY(launch_tc_layer(c, lzr, 2, segs, p));
+    RAFT_TRY(launch_tc_layer(c, lzr, 2, segs, p, -1, dep1(src_layer)));
   }
   {
     tc_params_init(p, EPI_GRU_Q, ACT_NONE, hid);
     p.z = W.z; p.h = h; p.hid = hid;
     p.out_hi = W.h_hi; p.out_lo = W.h_lo; p.h_stride = d.s_h; p.h_c0 = 0;
     TcSeg segs[2] = {{W.rh_hi, W.rh_lo, d.s_h, 0, d.s_h / kChunkK}, {W.x_hi, W.x_lo, d.s_x, 0, x_chunks}};
-    RAFT_TRY(launch_tc_layer(c, lq, 2, segs, p));
+    RAFT_TRY(launch_tc_layer(c, lq, 2, segs, p, -1, dep1(lzr)));
   }
   return 0;
-}
-
-// Side stream of the two-stream experiment (RAFT_B200_TWO_STREAMS=1): the flow branch of the motion encoder runs beside
-// the lookup + correlation branch of the same iteration and joins before `conv`.  Created once, on first use.
-struct SideStream { cudaStream_t s; cudaEvent_t fork, join; bool ok; };
-static SideStream& side_stream() {
-  static SideStream S = [] {
-    SideStream t;
-    memset(&t, 0, sizeof(t));
-    const char* e = getenv("RAFT_B200_TWO_STREAMS");
-    if (e && atoi(e) && cudaStreamCreateWithFlags(&t.s, cudaStreamNonBlocking) == cudaSuccess &&
-        cudaEventCreateWithFlags(&t.fork, cudaEventDisableTiming) == cudaSuccess &&
-        cudaEventCreateWithFlags(&t.join, cudaEventDisableTiming) == cudaSuccess)
-      t.ok = true;
-    return t;
-  }();
-  return S;
 }
 
 // Flow branch of BasicMotionEncoder (update.py:98-99): convf1 7x7 2->128 + relu, convf2 3x3 128->64 + relu ->
@@ -244,32 +255,13 @@ static int flow_branch_basic_tc(const UpdateCtx& c) {
     tc_params_init(p, EPI_LINEAR, ACT_RELU, 64);
     p.out_hi = W.cf_hi; p.out_lo = W.cf_lo; p.h_stride = d.s_cf; p.h_c0 = 192;
     TcSeg s[1] = {{W.flo1_hi, W.flo1_lo, d.s_flo1, 0, 2}};
-    RAFT_TRY(launch_tc_layer(c, 2, 1, s, p));
+    RAFT_TRY(launch_tc_layer(c, 2, 1, s, p, -1, dep1(11)));
   }
   return 0;
 }
 
-// flow_head.conv2 on CUDA cores from the fp16 operand planes (experiment, see flow_head2_kernel); returns false when
-// the knob is off and the caller should run the tensor-core layer.
-static bool fh2_simt(const UpdateCtx& c, int conv_idx, const __half* hi, const __half* lo, int cstride, int C, float* delta,
-                     int* status) {
-  static const int on = [] { const char* e = getenv("RAFT_B200_FH2_SIMT"); return e ? atoi(e) : 0; }();
-  if (!on || C % 32 != 0) return false;
-  FlowHead2Params q;
-  memset(&q, 0, sizeof(q));
-  q.hi = hi; q.lo = lo; q.cstride = cstride; q.c0 = 0; q.C = C;
-  q.w = reinterpret_cast<const float*>(c.prepared + c.PL.raw_w[conv_idx]);
-  q.bias = reinterpret_cast<const float*>(c.prepared + c.PL.raw_b[conv_idx]);
-  q.delta = delta; q.B = c.B; q.H = c.h; q.W = c.w;
-  const int tiles = c.B * ceil_div(c.h, 8) * ceil_div(c.w, 16);
-  flow_head2_kernel<<<tiles, 128, 0, c.stream>>>(q);
-  RAFT_COUNT_LAUNCH();
-  *status = raft_launch_status();
-  return true;
-}
-
-static int update_core_tc(const UpdateCtx& c, float* h, float* delta, float* mask, bool flow_done = false,
-                          cudaEvent_t flow_join = nullptr) {
+// adv_coords != null (iteration loop): the flow-head epilogue also applies coords1 += delta and flow = coords1 - grid.
+static int update_core_tc(const UpdateCtx& c, float* h, float* delta, float* mask, float* adv_coords = nullptr) {
   const Workspace& W = c.W;
   const VariantDims d = variant_dims(c.variant);
   TcConvParams p;
@@ -284,39 +276,36 @@ static int update_core_tc(const UpdateCtx& c, float* h, float* delta, float* mas
       tc_params_init(p, EPI_LINEAR, ACT_RELU, 192);
       p.out_hi = W.cf_hi; p.out_lo = W.cf_lo; p.h_stride = d.s_cf;
       TcSeg s[1] = {{W.cor1_hi, W.cor1_lo, d.s_cor1, 0, 4}};
-      RAFT_TRY(launch_tc_layer(c, 1, 1, s, p));
+      RAFT_TRY(launch_tc_layer(c, 1, 1, s, p, -1, dep1(0)));
     }
-    if (!flow_done) RAFT_TRY(flow_branch_basic_tc(c));      // convf1, convf2 (update.py:98-99)
-    else RAFT_CUDA_TRY(cudaStreamWaitEvent(c.stream, flow_join, 0));   // ... already running on the side stream
+    RAFT_TRY(flow_branch_basic_tc(c));                      // convf1, convf2 (update.py:98-99)
     {  // conv 3x3 256->126 + relu, concat flow -> x[128:256)
       tc_params_init(p, EPI_LINEAR, ACT_RELU, 126);
       p.out_hi = W.x_hi; p.out_lo = W.x_lo; p.h_stride = d.s_x; p.h_c0 = 128;
       p.concat_src = W.flow; p.concat_n = 2;
       TcSeg s[1] = {{W.cf_hi, W.cf_lo, d.s_cf, 0, 4}};
-      RAFT_TRY(launch_tc_layer(c, 3, 1, s, p));
+      RAFT_TRY(launch_tc_layer(c, 3, 1, s, p, -1, dep2(1, 2)));
     }
-    RAFT_TRY(gru_tc(c, h, 4, 5, 128, 4));
-    RAFT_TRY(gru_tc(c, h, 6, 7, 128, 4));
+    RAFT_TRY(gru_tc(c, h, 4, 5, 128, 4, 3));
+    RAFT_TRY(gru_tc(c, h, 6, 7, 128, 4, 5));
     {  // flow_head.conv1 || mask[0], 3x3 128->512 + relu
       tc_params_init(p, EPI_LINEAR, ACT_RELU, mask ? 512 : 256);
       p.out_hi = W.fm_hi; p.out_lo = W.fm_lo; p.h_stride = d.s_fm;
       TcSeg s[1] = {{W.h_hi, W.h_lo, d.s_h, 0, 2}};
-      RAFT_TRY(launch_tc_layer(c, 8, 1, s, p, mask ? 2 : 1));
+      RAFT_TRY(launch_tc_layer(c, 8, 1, s, p, mask ? 2 : 1, dep1(7)));
     }
-    int fh2_status = 0;
-    if (fh2_simt(c, BFH2, W.fm_hi, W.fm_lo, d.s_fm, 256, delta, &fh2_status)) {
-      RAFT_TRY(fh2_status);
-    } else {  // flow_head.conv2 3x3 256->2
+    {  // flow_head.conv2 3x3 256->2
       tc_params_init(p, EPI_LINEAR, ACT_NONE, 2);
       p.out_f32 = delta; p.f32_stride = 2;
+      p.adv_coords = adv_coords; p.adv_flow = adv_coords ? W.flow : nullptr;
       TcSeg s[1] = {{W.fm_hi, W.fm_lo, d.s_fm, 0, 4}};
-      RAFT_TRY(launch_tc_layer(c, 9, 1, s, p));
+      RAFT_TRY(launch_tc_layer(c, 9, 1, s, p, -1, dep1(8, 0)));
     }
     if (mask) {  // mask[2] 1x1 256->576, x0.25
       tc_params_init(p, EPI_LINEAR, ACT_NONE, 576);
       p.out_f32 = mask; p.f32_stride = 576; p.out_scale = 0.25f;
       TcSeg s[1] = {{W.fm_hi, W.fm_lo, d.s_fm, 256, 4}};
-      RAFT_TRY(launch_tc_layer(c, 10, 1, s, p));
+      RAFT_TRY(launch_tc_layer(c, 10, 1, s, p, -1, dep1(8, 1)));
     }
   } else {
     {  // convc1 1x1 196->96 + relu -> cor_flo[0:96)
@@ -338,30 +327,28 @@ static int update_core_tc(const UpdateCtx& c, float* h, float* delta, float* mas
       tc_params_init(p, EPI_LINEAR, ACT_RELU, 32);
       p.out_hi = W.cf_hi; p.out_lo = W.cf_lo; p.h_stride = d.s_cf; p.h_c0 = 96;
       TcSeg s[1] = {{W.flo1_hi, W.flo1_lo, d.s_flo1, 0, 1}};
-      RAFT_TRY(launch_tc_layer(c, 1, 1, s, p));
+      RAFT_TRY(launch_tc_layer(c, 1, 1, s, p, -1, dep1(7)));
     }
     {  // conv 3x3 128->80 + relu, concat flow -> x[64:160)
       tc_params_init(p, EPI_LINEAR, ACT_RELU, 80);
       p.out_hi = W.x_hi; p.out_lo = W.x_lo; p.h_stride = d.s_x; p.h_c0 = 64;
       p.concat_src = W.flow; p.concat_n = 2;
       TcSeg s[1] = {{W.cf_hi, W.cf_lo, d.s_cf, 0, 2}};
-      RAFT_TRY(launch_tc_layer(c, 2, 1, s, p));
+      RAFT_TRY(launch_tc_layer(c, 2, 1, s, p, -1, dep2(0, 1)));
     }
-    RAFT_TRY(gru_tc(c, h, 3, 4, 96, 3));
+    RAFT_TRY(gru_tc(c, h, 3, 4, 96, 3, 2));
     {  // flow_head.conv1 3x3 96->128 + relu
       tc_params_init(p, EPI_LINEAR, ACT_RELU, 128);
       p.out_hi = W.fm_hi; p.out_lo = W.fm_lo; p.h_stride = d.s_fm;
       TcSeg s[1] = {{W.h_hi, W.h_lo, d.s_h, 0, 2}};
-      RAFT_TRY(launch_tc_layer(c, 5, 1, s, p));
+      RAFT_TRY(launch_tc_layer(c, 5, 1, s, p, -1, dep1(4)));
     }
-    int fh2_status = 0;
-    if (fh2_simt(c, SFH2, W.fm_hi, W.fm_lo, d.s_fm, 128, delta, &fh2_status)) {
-      RAFT_TRY(fh2_status);
-    } else {  // flow_head.conv2 3x3 128->2
+    {  // flow_head.conv2 3x3 128->2
       tc_params_init(p, EPI_LINEAR, ACT_NONE, 2);
       p.out_f32 = delta; p.f32_stride = 2;
+      p.adv_coords = adv_coords; p.adv_flow = adv_coords ? W.flow : nullptr;
       TcSeg s[1] = {{W.fm_hi, W.fm_lo, d.s_fm, 0, 2}};
-      RAFT_TRY(launch_tc_layer(c, 6, 1, s, p));
+      RAFT_TRY(launch_tc_layer(c, 6, 1, s, p, -1, dep1(5)));
     }
   }
   return 0;
@@ -401,7 +388,25 @@ static int make_ctx(UpdateCtx& c, int variant, const void* prepared, int B, int 
   c.W = workspace_layout(ws, variant, B, h, w, precision);
   if (c.W.total > ws_bytes) return RAFT_ERR_WORKSPACE;
   c.stream = reinterpret_cast<cudaStream_t>(stream);
+  c.plan = nullptr;
   return 0;
+}
+
+// One update_mega_kernel launch for all tensor-core layers of an update-block application (default), or one launch per
+// layer (RAFT_B200_MEGA=0: A/B timing and bisecting).
+static bool mega_enabled() {
+  static const int v = [] { const char* e = getenv("RAFT_B200_MEGA"); return e ? atoi(e) : 1; }();
+  return v != 0;
+}
+static int update_block_tc(UpdateCtx& c, float* h, float* delta, float* mask, float* adv_coords) {
+  MegaPlan plan;
+  c.plan = mega_enabled() ? &plan : nullptr;
+  const int st = update_core_tc(c, h, delta, mask, adv_coords);
+  c.plan = nullptr;
+  RAFT_TRY(st);
+  if (!mega_enabled()) return 0;
+  RAFT_COUNT_LAUNCH();
+  return mega_launch(plan, c.W.mega_flags, c.W.mega_flag_words, true, c.stream);
 }
 
 static int update_once(int variant, const void* prepared, const float* net, const float* inp, const float* corr,
@@ -420,7 +425,7 @@ static int update_once(int variant, const void* prepared, const float* net, cons
     split_plane_kernel<<<grid_for(npix * d.s_corr), 256, 0, c.stream>>>(corr, d.corr_ch, 0, d.corr_ch, d.s_corr,
                                                                          c.W.corr_hi, c.W.corr_lo, d.s_corr, 0, npix, 1.0f);
     RAFT_COUNT_LAUNCH();
-    return update_core_tc(c, net_out, delta, mask);
+    return update_block_tc(c, net_out, delta, mask, nullptr);
   }
   RAFT_CUDA_TRY(cudaMemcpyAsync(c.W.corr, corr, npix * d.corr_ch * sizeof(float), cudaMemcpyDeviceToDevice, c.stream));
   return update_core_fp32(c, net_out, delta, mask);
@@ -445,11 +450,8 @@ static int lookup_launch(const float* const pyr[], const float* coords, int B, i
   p.out_hi = out_hi; p.out_lo = out_lo; p.h_stride = h_stride; p.h_pad = h_pad;
   p.nq = B * h * w; p.levels = levels; p.radius = radius;
   const size_t nwork = (size_t)p.nq * levels;
-  static const int v2 = [] { const char* e = getenv("RAFT_B200_LOOKUP_V2"); return e ? atoi(e) : 0; }();
-  if (v2 && levels == 4 && (radius == 4 || radius == 3) && nwork < (1u << 31)) {   // experiment: compile-time radius / levels
-    if (radius == 4) corr_lookup_fixed_kernel<4, 4><<<grid_for(nwork * 32, 256, kNumSMs * 32), 256, 0, st>>>(p);
-    else corr_lookup_fixed_kernel<3, 4><<<grid_for(nwork * 32, 256, kNumSMs * 32), 256, 0, st>>>(p);
-  } else
+  static const int gather = [] { const char* e = getenv("RAFT_B200_LOOKUP_GATHER"); return e ? atoi(e) : 0; }();   // A/B: force the generic kernel
+  if (gather || !lookup_win_launch(p, levels, radius, st))         // window kernel for the model's (radius, levels); else generic
     corr_lookup_kernel<<<grid_for(nwork * 32, 256, kNumSMs * 32), 256, 0, st>>>(p);
   RAFT_COUNT_LAUNCH();
   return raft_launch_status();
@@ -759,25 +761,15 @@ int raft_b200_forward_loop(int variant, const void* prepared, const float* const
   for (int i = 0; i < iters; ++i) {
     float* mask = (variant == RAFT_VARIANT_BASIC && flow_up[i]) ? W.mask : nullptr;
     if (precision == RAFT_PREC_F16X2) {
-      SideStream& S = side_stream();
-      const bool fork = S.ok && variant == RAFT_VARIANT_BASIC;
-      if (fork) {   // experiment: flow branch on the side stream, beside the lookup and the correlation branch
-        RAFT_CUDA_TRY(cudaEventRecord(S.fork, c.stream));
-        RAFT_CUDA_TRY(cudaStreamWaitEvent(S.s, S.fork, 0));
-        UpdateCtx c2 = c;
-        c2.stream = S.s;
-        RAFT_TRY(flow_branch_basic_tc(c2));
-        RAFT_CUDA_TRY(cudaEventRecord(S.join, S.s));
-      }
       RAFT_TRY(lookup_launch(pyr, coords1, B, h, w, levels, radius, nullptr, 0, W.corr_hi, W.corr_lo, d.s_corr, d.s_corr,
                              c.stream));                                                            // model.py:95
-      RAFT_TRY(update_core_tc(c, net, W.delta, mask, fork, S.join));                                // :99
+      RAFT_TRY(update_block_tc(c, net, W.delta, mask, coords1));                                    // :99, :102 (fused advance)
     } else {
       RAFT_TRY(lookup_launch(pyr, coords1, B, h, w, levels, radius, W.corr, d.corr_ch, nullptr, nullptr, 0, 0, c.stream));
       RAFT_TRY(update_core_fp32(c, net, W.delta, mask));
+      flow_advance_kernel<<<grid_for(npix), 256, 0, c.stream>>>(coords1, W.delta, W.flow, B, h, w);  // :102
+      RAFT_COUNT_LAUNCH();
     }
-    flow_advance_kernel<<<grid_for(npix), 256, 0, c.stream>>>(coords1, W.delta, W.flow, B, h, w);  // :102
-    RAFT_COUNT_LAUNCH();
     if (flow_up[i]) {                                                                               // :105 / :223
       if (variant == RAFT_VARIANT_BASIC)
         RAFT_TRY(raft_b200_upsample_convex(W.flow, W.mask, B, h, w, flow_up[i], stream));

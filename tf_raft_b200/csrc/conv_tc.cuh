@@ -92,6 +92,10 @@ struct alignas(64) TcConvParams {
   // instead of 8 x 512-byte store instructions; rows / columns past the level's extent are clipped by the TMA unit.
   int out_tma;
   CUtensorMap out_map;
+  // EPI_LINEAR with n_total == 2 (flow_head.conv2) inside the iteration loop: coords1 += delta_flow and
+  // flow = coords1 - coords0 (model.py:102, :97) are applied by the thread that holds the pixel's two output columns.
+  float* adv_coords;                       // (px, 2) coords1, updated in place; null = no fused advance
+  float* adv_flow;                         // (px, 2) coords1 - pixel grid
 };
 
 #if defined(__CUDA_ARCH__)
@@ -99,6 +103,9 @@ struct alignas(64) TcConvParams {
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+// L2-coherent 16-byte load (ld.global.cg): z and h may have been written by another CTA of the SAME grid (update_mega_kernel),
+// so they must not be served from this SM's L1 nor through the non-coherent path.
+__device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
@@ -186,6 +193,14 @@ __device__ __forceinline__ void tc_epilogue_regs(const TcConvParams& p, float (&
       dhi = p.out_hi + o;
       dlo = p.out_lo + o;
     }
+    if (p.adv_coords && col == 0) {                    // model.py:102: coords1 += delta; flow = coords1 - coords0 (pixel grid)
+      float2 c1 = __ldcg(reinterpret_cast<const float2*>(p.adv_coords) + pix);
+      c1.x = __fadd_rn(c1.x, v[0]);
+      c1.y = __fadd_rn(c1.y, v[1]);
+      reinterpret_cast<float2*>(p.adv_coords)[pix] = c1;
+      const float gx = (float)(pix % p.W), gy = (float)((pix / p.W) % p.H);
+      reinterpret_cast<float2*>(p.adv_flow)[pix] = make_float2(__fsub_rn(c1.x, gx), __fsub_rn(c1.y, gy));
+    }
   } else if (MODE == EPI_GRU_ZR) {
     if (col < p.hid) {                                 // z gate -> fp32 plane
       float* dst = p.z + pix * (size_t)p.hid + col;
@@ -198,7 +213,7 @@ __device__ __forceinline__ void tc_epilogue_regs(const TcConvParams& p, float (&
       const float* hp = p.h + pix * (size_t)p.hid + hc;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const float4 hv = ldg4(hp + 4 * q);
+        const float4 hv = ldcg4(hp + 4 * q);
         v[4 * q] = fast_sigmoid(v[4 * q]) * hv.x; v[4 * q + 1] = fast_sigmoid(v[4 * q + 1]) * hv.y;
         v[4 * q + 2] = fast_sigmoid(v[4 * q + 2]) * hv.z; v[4 * q + 3] = fast_sigmoid(v[4 * q + 3]) * hv.w;
       }
@@ -211,7 +226,7 @@ __device__ __forceinline__ void tc_epilogue_regs(const TcConvParams& p, float (&
     const float* zp = p.z + pix * (size_t)p.hid + col;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      const float4 zv = ldg4(zp + 4 * q), hv = ld4(hrow + 4 * q);
+      const float4 zv = ldcg4(zp + 4 * q), hv = ldcg4(hrow + 4 * q);
       v[4 * q] = (1.0f - zv.x) * hv.x + zv.x * fast_tanh(v[4 * q]);
       v[4 * q + 1] = (1.0f - zv.y) * hv.y + zv.y * fast_tanh(v[4 * q + 1]);
       v[4 * q + 2] = (1.0f - zv.z) * hv.z + zv.z * fast_tanh(v[4 * q + 2]);
@@ -290,8 +305,8 @@ __device__ __forceinline__ void tc_epilogue_q_t(const TcConvParams& p, float (&v
 #pragma unroll
       for (int kk = 0; kk < 2; ++kk) {
         const bool ok = pixr[k0 + kk] >= 0;
-        zv[kk] = ok ? ldg4(p.z + (size_t)pixr[k0 + kk] * p.hid + col) : make_float4(0.f, 0.f, 0.f, 0.f);
-        hv[kk] = ok ? ld4(p.h + (size_t)pixr[k0 + kk] * p.hid + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+        zv[kk] = ok ? ldcg4(p.z + (size_t)pixr[k0 + kk] * p.hid + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+        hv[kk] = ok ? ldcg4(p.h + (size_t)pixr[k0 + kk] * p.hid + col) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
       for (int kk = 0; kk < 2; ++kk) {

@@ -7,6 +7,7 @@
 // 'instance' (and 'batch' in training) need statistics of the raw conv output: two deterministic reduction
 // passes + one apply kernel that also does ReLU, the residual add and the fp16 hi/lo re-split.
 #pragma once
+#include "lookup.cuh"
 #include "update.cuh"
 
 namespace raft {

@@ -199,77 +199,6 @@ __global__ void __launch_bounds__(256) corr_lookup_kernel(const LookupParams p) 
   }
 }
 
-// Same lookup with the radius and the level count fixed at compile time (experiment, RAFT_B200_LOOKUP_V2=1; the kernel
-// above is instruction-issue bound -- 469 warp instructions per (query, level), mostly 64-bit address arithmetic and
-// divisions by the run-time window side).  Identical floating-point operations in identical order: bit-identical output.
-template <int kRadius, int kLevels>
-__global__ void __launch_bounds__(256) corr_lookup_fixed_kernel(const LookupParams p) {
-  constexpr int side = 2 * kRadius + 1, ntap = side * side, kIter = (ntap + 31) / 32;
-  static_assert(side <= 16, "axis set-ups are kept in 16 + 16 shared-memory slots per warp");
-  __shared__ float4 axis_smem[8 * 32];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const unsigned nwork = (unsigned)p.nq * kLevels;                // host guarantees nq * levels < 2^31
-  float4* ax = axis_smem + wib * 32;                              // [0,16): x set-ups, [16,32): y set-ups
-  for (unsigned wi = blockIdx.x * 8u + wib; wi < nwork; wi += gridDim.x * 8u) {
-    const int q = (int)(wi / kLevels), l = (int)(wi % kLevels);
-    const int H = p.lh[l], W = p.lw[l];
-    const float* img = p.pyr[l] + (size_t)q * H * W;
-    const float inv = 1.0f / (float)(1 << l);                     // exact power of two
-    const float cx = __fmul_rn(__ldg(p.coords + 2 * (size_t)q), inv);       // coords / 2**i  (corr.py:141)
-    const float cy = __fmul_rn(__ldg(p.coords + 2 * (size_t)q + 1), inv);
-    __syncwarp();
-    if (lane < 2 * side) {
-      const bool isy = lane >= side;
-      const int i = isy ? lane - side : lane;
-      const float cc = isy ? cy : cx;
-      const int dim = isy ? H : W;
-      const float g = fminf(fmaxf(__fadd_rn(cc, (float)(i - kRadius)), 0.0f), (float)(dim - 1));   // centroid + delta, clamp
-      const float g0 = floorf(g), g1 = ceilf(g);
-      ax[(isy ? 16 : 0) + i] = make_float4(__fsub_rn(g1, g), __fsub_rn(g, g0), __int_as_float((int)g0), __int_as_float((int)g1));
-    }
-    __syncwarp();
-    TapGather tg[kIter];
-    float x00[kIter], x01[kIter], x10[kIter], x11[kIter];
-#pragma unroll
-    for (int i = 0; i < kIter; ++i) {
-      const int t = min(lane + 32 * i, ntap - 1);
-      const int a = t / side, b2 = t - a * side;                  // compile-time divisor
-      const float4 sx = ax[a], sy = ax[16 + b2];                  // (w1, w0, i0, i1) per axis
-      const int ix0 = __float_as_int(sx.z), ix1 = __float_as_int(sx.w);
-      const float* r0 = img + __float_as_int(sy.z) * W;
-      const float* r1 = img + __float_as_int(sy.w) * W;
-      tg[i].c00 = __fmul_rn(sy.x, sx.x); tg[i].c01 = __fmul_rn(sy.x, sx.y);
-      tg[i].c10 = __fmul_rn(sy.y, sx.x); tg[i].c11 = __fmul_rn(sy.y, sx.y);
-      x00[i] = __ldg(r0 + ix0); x01[i] = __ldg(r0 + ix1);
-      x10[i] = __ldg(r1 + ix0); x11[i] = __ldg(r1 + ix1);
-    }
-    float* o = p.out ? p.out + (size_t)q * p.out_stride + l * ntap : nullptr;
-    __half* oh = p.out_hi ? p.out_hi + (size_t)q * p.h_stride + l * ntap : nullptr;
-    __half* ol = p.out_hi ? p.out_lo + (size_t)q * p.h_stride + l * ntap : nullptr;
-#pragma unroll
-    for (int i = 0; i < kIter; ++i) {
-      const int t = lane + 32 * i;
-      if (t < ntap) {
-        const float v = tap_combine(tg[i], x00[i], x01[i], x10[i], x11[i]);
-        if (o) o[t] = v;
-        if (oh) {
-          __half hh, ll;
-          split_f16(v, hh, ll);
-          oh[t] = hh;
-          ol[t] = ll;
-        }
-      }
-    }
-    if (oh && l == kLevels - 1) {
-      const __half zero = __float2half_rn(0.f);
-      for (int c = ntap + lane; c < p.h_pad - l * ntap; c += 32) {   // channels [levels * ntap, h_pad) of the operand planes
-        oh[c] = zero;
-        ol[c] = zero;
-      }
-    }
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
 // flow_head.conv2 (update.py:11,14): 3x3 'same' convolution, C hidden channels -> the 2 flow-delta channels, read from
 // the fp16 hi/lo operand planes of the hidden activation, fp32 FFMA accumulation (experiment, RAFT_B200_FH2_SIMT=1).

@@ -5,6 +5,7 @@
 
 #include "conv_tc.cuh"
 #include "kernels.cuh"
+#include "mega.cuh"
 
 namespace raft {
 
@@ -139,6 +140,7 @@ struct Workspace {
   __half *corr_hi, *corr_lo, *cor1_hi, *cor1_lo, *cf_hi, *cf_lo, *flo1_hi, *flo1_lo, *x_hi, *x_lo, *h_hi, *h_lo,
       *rh_hi, *rh_lo, *fm_hi, *fm_lo, *fim_hi, *fim_lo;
   uint8_t* f16_begin; size_t f16_bytes;
+  unsigned int* mega_flags; size_t mega_flag_words;   // per-(layer, tile) completion counters of update_mega_kernel
   size_t total;
 };
 
@@ -186,6 +188,10 @@ inline Workspace workspace_layout(void* base, int variant, int B, int h, int w, 
     W.fm_hi = f16(d.s_fm); W.fm_lo = f16(d.s_fm);
     W.fim_hi = f16(128); W.fim_lo = f16(128);      // im2col of the 7x7 flow window (98 -> 128 channels)
     W.f16_bytes = (size_t)((b8 + off) - W.f16_begin);
+    // any 128-pixel tile shape covers an h x w plane with at most h*w/128 + h + w + 1 tiles
+    W.mega_flag_words = (size_t)mega_flag_words(B, h * w / 128 + h + w + 1);
+    W.mega_flags = reinterpret_cast<unsigned int*>(b8 + off);
+    off = align_up(off + W.mega_flag_words * sizeof(unsigned int), 1024);
   }
   W.total = off;
   return W;
@@ -200,6 +206,7 @@ struct UpdateCtx {
   PreparedLayout PL;
   Workspace W;
   cudaStream_t stream;
+  MegaPlan* plan;      // non-null: tensor-core layers are collected here and run as ONE update_mega_kernel launch
 };
 
 inline int launch_simt_conv(const UpdateCtx& c, int conv_idx, int nsrc, const float* const src[], const int src_stride[],
@@ -250,7 +257,8 @@ inline int simt2(const UpdateCtx& c, int conv_idx, const float* s0, int st0, int
 // first channel, number of 64-channel chunks).
 struct TcSeg { const __half* hi; const __half* lo; int stride, c0, chunks; };
 
-inline int launch_tc_layer(const UpdateCtx& c, int layer, int nseg, const TcSeg* segs, TcConvParams& p, int ntn = -1) {
+inline int launch_tc_layer(const UpdateCtx& c, int layer, int nseg, const TcSeg* segs, TcConvParams& p, int ntn = -1,
+                           const TcDeps& deps = TcDeps{0, {-1, -1}, {-1, -1}}) {
   const TcLayerSpec& L = tc_layers(c.variant)[layer];
   int tw, th;
   tc_pick_tile(c.w, c.h, &tw, &th);
@@ -278,6 +286,7 @@ inline int launch_tc_layer(const UpdateCtx& c, int layer, int nseg, const TcSeg*
     static const int grp = [] { const char* e = getenv("RAFT_B200_UPD_GROUP"); return e ? atoi(e) : 0; }();
     if (grp > 0) p.group_chunks = grp;
   }
+  if (c.plan) return mega_add(*c.plan, layer, p, ntn > 0 ? ntn : L.ntn, deps);
   RAFT_COUNT_LAUNCH();
   return tc_launch(p, ntn > 0 ? ntn : L.ntn, c.stream);
 }

@@ -86,6 +86,23 @@ int raft_b200_corr_pyramid_build(const float* fmap1, const float* fmap2, int B, 
 int raft_b200_corr_lookup(const float* const pyr[], const float* coords, int B, int h, int w, int levels,
                           int radius, float* out, int out_stride, void* stream);
 
+/* Backward of CorrBlock.retrieve for the training step (tf_raft/model.py:133: tape.gradient through corr.py:116-152;
+ * the reference does not detach coords1, model.py:102).  grad_out (B, h, w, levels*(2r+1)^2) -> grad_coords (B, h, w, 2)
+ * and grad_pyr[l] (same shapes as pyr[l]); both outputs are ACCUMULATED into (zero them first).  TensorFlow gradient
+ * rules: floor / ceil / indices carry no gradient, clip_by_value passes it inside [0, dim-1].                        */
+int raft_b200_corr_lookup_backward(const float* const pyr[], const float* coords, const float* grad_out, int B, int h, int w,
+                                   int levels, int radius, float* grad_coords, float* const grad_pyr[], void* stream);
+
+/* tf.linalg.global_norm over a flat gradient buffer (model.py:135): out[0] = sum g^2 (deterministic two-stage
+ * reduction; `partials` holds one float per block, at most npartials blocks are used).                               */
+int raft_b200_sumsq(const float* g, size_t n, float* partials, size_t npartials, float* out, void* stream);
+
+/* tf.clip_by_global_norm (model.py:135) + tfa.optimizers.AdamW.apply_gradients (model.py:136, train_chairs.py:87-90)
+ * on flat buffers: g' = g * clip / max(sqrt(*sumsq), clip) (clip_norm <= 0: no clipping); var -= wd * var;
+ * m = b1 m + (1-b1) g'; v = b2 v + (1-b2) g'^2; var -= lr_t * m / (sqrt(v) + eps), lr_t already bias-corrected.        */
+int raft_b200_adamw_step(float* param, const float* grad, float* m, float* v, size_t n, const float* sumsq, float clip_norm,
+                         float lr_t, float beta1, float beta2, float epsilon, float weight_decay, void* stream);
+
 /* bilinear_sampler(image, coords): corr.py:28-69.  image (M, H, W, 1), coords (M, P, 2),
  * out (M, P).  Same floor/ceil semantics as above.                                             */
 int raft_b200_bilinear_sampler(const float* image, const float* coords, int M, int H, int W, int P, float* out,

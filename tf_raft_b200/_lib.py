@@ -68,6 +68,10 @@ _SIGNATURES = {
     'raft_b200_corr_workspace_bytes': (_i, [_i, _i, _i, _i, _i, _i, ctypes.POINTER(_sz)]),
     'raft_b200_corr_pyramid_build': (_i, [_vp, _vp, _i, _i, _i, _i, _i, ctypes.POINTER(_vp), _vp, _sz, _i, _vp]),
     'raft_b200_corr_lookup': (_i, [ctypes.POINTER(_vp), _vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    'raft_b200_corr_lookup_backward': (_i, [ctypes.POINTER(_vp), _vp, _vp, _i, _i, _i, _i, _i, _vp, ctypes.POINTER(_vp), _vp]),
+    'raft_b200_sumsq': (_i, [_vp, _sz, _vp, _sz, _vp, _vp]),
+    'raft_b200_adamw_step': (_i, [_vp, _vp, _vp, _vp, _sz, _vp, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                  ctypes.c_float, ctypes.c_float, ctypes.c_float, _vp]),
     'raft_b200_bilinear_sampler': (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     'raft_b200_coords_grid': (_i, [_i, _i, _i, _vp, _vp]),
     'raft_b200_update_prepared_bytes': (_i, [_i, _i, _i, ctypes.POINTER(_sz)]),

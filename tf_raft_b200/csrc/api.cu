@@ -5,6 +5,7 @@
 
 #include "corr_tc.cuh"
 #include "encoder.cuh"
+#include "train.cuh"
 
 namespace raft {
 thread_local long long g_launches = 0;
@@ -543,6 +544,50 @@ int raft_b200_corr_lookup(const float* const pyr[], const float* coords, int B, 
   if (out_stride < levels * side * side) return RAFT_ERR_BAD_SHAPE;
   return lookup_launch(pyr, coords, B, h, w, levels, radius, out, out_stride, nullptr, nullptr, 0, 0,
                        reinterpret_cast<cudaStream_t>(stream));
+}
+
+int raft_b200_corr_lookup_backward(const float* const pyr[], const float* coords, const float* grad_out, int B, int h, int w,
+                                   int levels, int radius, float* grad_coords, float* const grad_pyr[], void* stream) {
+  if (!pyr || !coords || !grad_out || !grad_coords || !grad_pyr || levels < 1 || levels > RAFT_MAX_LEVELS || radius < 0)
+    return RAFT_ERR_BAD_ARG;
+  RAFT_TRY(check_dims(B, h, w));
+  LookupBwdParams p;
+  memset(&p, 0, sizeof(p));
+  int lh = h, lw = w;
+  for (int l = 0; l < levels; ++l) {
+    if (lh < 1 || lw < 1) return RAFT_ERR_BAD_SHAPE;
+    if (!pyr[l] || !grad_pyr[l]) return RAFT_ERR_BAD_ARG;
+    p.pyr[l] = pyr[l]; p.gpyr[l] = grad_pyr[l]; p.lh[l] = lh; p.lw[l] = lw;
+    lh /= 2;
+    lw /= 2;
+  }
+  const int side = 2 * radius + 1;
+  p.coords = coords; p.gout = grad_out; p.gout_stride = levels * side * side; p.gcoords = grad_coords;
+  p.nq = B * h * w; p.levels = levels; p.radius = radius;
+  const size_t nwork = (size_t)p.nq * levels;
+  corr_lookup_bwd_kernel<<<grid_for(nwork * 32, 256, kNumSMs * 32), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  RAFT_COUNT_LAUNCH();
+  return raft_launch_status();
+}
+
+int raft_b200_sumsq(const float* g, size_t n, float* partials, size_t npartials, float* out, void* stream) {
+  if (!g || !partials || !out || npartials < 1) return RAFT_ERR_BAD_ARG;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int blocks = (int)std::min<size_t>(std::min<size_t>(npartials, (size_t)kNumSMs * 4), (n + 255) / 256);
+  if (blocks < 1) blocks = 1;
+  sumsq_partial_kernel<<<blocks, 256, 0, st>>>(g, n, partials);
+  sumsq_final_kernel<<<1, 256, 0, st>>>(partials, blocks, out);
+  g_launches += 2;
+  return raft_launch_status();
+}
+
+int raft_b200_adamw_step(float* param, const float* grad, float* m, float* v, size_t n, const float* sumsq, float clip_norm,
+                         float lr_t, float beta1, float beta2, float epsilon, float weight_decay, void* stream) {
+  if (!param || !grad || !m || !v || (clip_norm > 0.0f && !sumsq)) return RAFT_ERR_BAD_ARG;
+  adamw_kernel<<<grid_for(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(param, grad, m, v, n, sumsq, clip_norm, lr_t,
+                                                                             beta1, beta2, epsilon, weight_decay);
+  RAFT_COUNT_LAUNCH();
+  return raft_launch_status();
 }
 
 int raft_b200_bilinear_sampler(const float* image, const float* coords, int M, int H, int W, int P, float* out,

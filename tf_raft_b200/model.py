@@ -36,6 +36,9 @@ class RAFT:
         self._build_layers(seed)
         self._graphs = {}
         self.flow_metrics = None
+        self.optimizer = None
+        self._trainer = None
+        self._params_stale = False
 
     def _encoder_backend(self):
         # the all-FFMA reference configuration keeps cuDNN IEEE-fp32 encoders; the product path is native
@@ -57,8 +60,11 @@ class RAFT:
         self.cnet.load_params(params, 'cnet.')
         self.update_block.load_params(params, 'update_block.')
         self._graphs.clear()
+        self._trainer = None                               # a training state built on the old values is void
+        self._params_stale = False
 
     def state_dict(self):
+        self._sync_trained_params()
         out = OrderedDict()
         out.update(self.fnet.state_dict('fnet.'))
         out.update(self.cnet.state_dict('cnet.'))
@@ -115,6 +121,7 @@ class RAFT:
         and replayed; the returned tensors are then static buffers that the next call overwrites."""
         image1, image2 = inputs
         image1, image2 = _lib.f32c(image1), _lib.f32c(image2)
+        self._sync_trained_params()
         if self.use_graph and not training:
             return self._graph_call(image1, image2, last_only)
         return self._forward(image1, image2, training, last_only)
@@ -183,9 +190,30 @@ class RAFT:
         return {k: (s / n if n else 0.0) for k, (s, n) in self.flow_metrics.items()}
 
     def train_step(self, data):
-        raise NotImplementedError(
-            'train_step needs the backward pass of the CUDA kernels (SURVEY.md section 8(f) rank 2); this round '
-            'implements the forward/update hot path only')
+        """model.py:126-144: forward with training=True under autograd, sequence loss, clip_by_global_norm,
+        optimizer.apply_gradients, metrics.  data = (image1, image2, flow_gt, valid) on the GPU.  Under an initialised
+        torch.distributed process group the gradients are all-reduced (one flat NCCL call) and the context encoder's
+        BatchNorm statistics are taken over the global batch (tf_raft_b200/train.py)."""
+        from .train import AdamW, Trainer
+        if self.flow_metrics is None or getattr(self, 'optimizer', None) is None:
+            raise RuntimeError('compile(optimizer=..., clip_norm=...) before train_step, as in train_chairs.py:92-98')
+        if not isinstance(self.optimizer, AdamW):
+            raise TypeError('optimizer must be tf_raft_b200.train.AdamW (tfa.optimizers.AdamW semantics)')
+        if self._trainer is None:
+            self._trainer = Trainer(self)
+        loss, info = self._trainer.step(data, self.optimizer, self.clip_norm, self.loss, self.epe)
+        self._params_stale = True                      # the layers' own copies are refreshed on the next inference call
+        self._metric_update('loss', loss)
+        for k in ('epe', 'u1', 'u3', 'u5'):
+            self._metric_update(k, info[k])
+        return self._metric_results()
+
+    def _sync_trained_params(self):
+        if self._trainer is not None and self._params_stale:
+            trainer = self._trainer
+            self.load_params(trainer.params())         # copies into the layers, drops prepared blobs and graphs
+            self._trainer = trainer
+            self._params_stale = False
 
     def test_step(self, data):
         """model.py:146-159."""

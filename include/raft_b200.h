@@ -249,7 +249,12 @@ int raft_b200_forward_loop(int variant, const void* prepared, const float* const
 /* Number of kernels the most recent call on this host thread launched (bench.py's gpu_launches). */
 long long raft_b200_launch_count(void);
 void raft_b200_launch_count_reset(void);
-/* Profiling aid: the next update-block launches of tensor-core layer `tc_layer` (-1 = off) write clock64 stamps of
+/* Profiling aid for bench.py's roofline objects: while enabled, raft_b200_forward_loop (F16X2, <= 64 iterations, not
+ * under CUDA-graph capture) records CUDA events on its stream around the lookup and around the update-block kernel(s)
+ * of every iteration; _read waits for the last one and returns the summed durations of the most recent call.      */
+void raft_b200_profile_loop(int enable);
+int raft_b200_profile_read(float* lookup_ms, float* update_ms, int* iterations);
+/* Profiling aid: the next update-block launches of tensor-core layer `tc_layer` (-1 = off; 2000 = the correlation kernel) write clock64 stamps of
  * CTA 0 into `device_buf_2048` (4 x 512 int64: slot free / data landed / group retired / group drained).        */
 void raft_b200_debug_timeline(int tc_layer, long long* device_buf_2048);
 

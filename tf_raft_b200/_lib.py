@@ -64,6 +64,8 @@ _SIGNATURES = {
     'raft_b200_launch_count': (ctypes.c_longlong, []),
     'raft_b200_launch_count_reset': (None, []),
     'raft_b200_debug_timeline': (None, [_i, _vp]),
+    'raft_b200_profile_loop': (None, [_i]),
+    'raft_b200_profile_read': (_i, [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_i)]),
     'raft_b200_corr_pyramid_sizes': (_i, [_i, _i, _i, _i, ctypes.POINTER(_sz)]),
     'raft_b200_corr_workspace_bytes': (_i, [_i, _i, _i, _i, _i, _i, ctypes.POINTER(_sz)]),
     'raft_b200_corr_pyramid_build': (_i, [_vp, _vp, _i, _i, _i, _i, _i, ctypes.POINTER(_vp), _vp, _sz, _i, _vp]),

@@ -15,6 +15,17 @@ int g_dbg_count = 0;               // encoder convolutions launched since the ti
 
 static int check_dims(int B, int h, int w) { return (B > 0 && h > 0 && w > 0) ? 0 : RAFT_ERR_BAD_SHAPE; }
 
+// Per-kernel timing of raft_b200_forward_loop for bench.py's roofline objects: CUDA events on the launching stream around
+// the lookup and around the update-block kernel(s) of every iteration (raft_b200_profile_loop / _read).  Off by default;
+// never armed while a CUDA graph is being captured.
+struct LoopProfile {
+  bool on = false;
+  int n = 0;                                   // iterations recorded by the last forward_loop call
+  cudaEvent_t ev[64][3];                       // [iteration]: before lookup, after lookup (+ im2col), after the update block
+  bool created = false;
+};
+static LoopProfile g_prof;
+
 // ------------------------------------------------------------------------------------------------
 // Correlation pyramid
 // ------------------------------------------------------------------------------------------------
@@ -491,6 +502,21 @@ int raft_b200_device_ok(int device) {
   return major == 10 ? RAFT_OK : RAFT_ERR_NO_DEVICE;
 }
 
+void raft_b200_profile_loop(int enable) { g_prof.on = enable != 0; g_prof.n = 0; }
+int raft_b200_profile_read(float* lookup_ms, float* update_ms, int* iterations) {
+  if (!lookup_ms || !update_ms || !iterations) return RAFT_ERR_BAD_ARG;
+  *lookup_ms = 0.f; *update_ms = 0.f; *iterations = g_prof.n;
+  for (int i = 0; i < g_prof.n; ++i) {
+    float a = 0.f, b = 0.f;
+    RAFT_CUDA_TRY(cudaEventSynchronize(g_prof.ev[i][2]));
+    RAFT_CUDA_TRY(cudaEventElapsedTime(&a, g_prof.ev[i][0], g_prof.ev[i][1]));
+    RAFT_CUDA_TRY(cudaEventElapsedTime(&b, g_prof.ev[i][1], g_prof.ev[i][2]));
+    *lookup_ms += a;
+    *update_ms += b;
+  }
+  return RAFT_OK;
+}
+
 long long raft_b200_launch_count(void) { return g_launches; }
 void raft_b200_debug_timeline(int tc_layer, long long* device_buf_2048) {
   g_dbg_layer = tc_layer;
@@ -803,12 +829,22 @@ int raft_b200_forward_loop(int variant, const void* prepared, const float* const
   RAFT_TRY(update_begin(c, net, inp));
   flow_advance_kernel<<<grid_for(npix), 256, 0, c.stream>>>(coords1, nullptr, W.flow, B, h, w);   // model.py:97
   RAFT_COUNT_LAUNCH();
+  const bool prof = g_prof.on && iters <= 64;
+  if (prof && !g_prof.created) {
+    for (int i = 0; i < 64; ++i)
+      for (int k = 0; k < 3; ++k) RAFT_CUDA_TRY(cudaEventCreate(&g_prof.ev[i][k]));
+    g_prof.created = true;
+  }
+  if (prof) g_prof.n = iters;
   for (int i = 0; i < iters; ++i) {
     float* mask = (variant == RAFT_VARIANT_BASIC && flow_up[i]) ? W.mask : nullptr;
     if (precision == RAFT_PREC_F16X2) {
+      if (prof) RAFT_CUDA_TRY(cudaEventRecord(g_prof.ev[i][0], c.stream));
       RAFT_TRY(lookup_launch(pyr, coords1, B, h, w, levels, radius, nullptr, 0, W.corr_hi, W.corr_lo, d.s_corr, d.s_corr,
                              c.stream));                                                            // model.py:95
+      if (prof) RAFT_CUDA_TRY(cudaEventRecord(g_prof.ev[i][1], c.stream));
       RAFT_TRY(update_block_tc(c, net, W.delta, mask, coords1));                                    // :99, :102 (fused advance)
+      if (prof) RAFT_CUDA_TRY(cudaEventRecord(g_prof.ev[i][2], c.stream));
     } else {
       RAFT_TRY(lookup_launch(pyr, coords1, B, h, w, levels, radius, W.corr, d.corr_ch, nullptr, nullptr, 0, 0, c.stream));
       RAFT_TRY(update_core_fp32(c, net, W.delta, mask));

@@ -32,16 +32,14 @@ enum TcEpilogue : int {
   EPI_LINEAR = 0,  // v = act(acc*inv_scale + bias) * out_scale  -> optional fp32 and/or fp16 hi/lo planes
   EPI_GRU_ZR = 1,  // cols [0,hid): z = sigmoid(v) -> z plane; cols [hid,2hid): r = sigmoid(v), r*h -> hi/lo planes
   EPI_GRU_Q = 2,   // q = tanh(v); h = (1-z)*h + z*q -> h fp32 (in place) + hi/lo planes
-  EPI_CORR = 3,    // v = acc / sqrt(C) -> fp32 pyramid level rows
 };
 enum TcAct : int { ACT_NONE = 0, ACT_RELU = 1 };
 
 constexpr int kEpiWarpsConv = 16;         // promotion/epilogue warps of the convolution instantiation (4 per TMEM lane quarter)
-constexpr int kEpiWarpsCorr = 8;          // ... of the correlation instantiation (each needs a 4 KB transposition patch)
 constexpr int kTileM = 128;
 constexpr int kChunkK = 64;                       // fp16 elements per 128-byte swizzled row
 constexpr int kABytes = kTileM * kChunkK * 2;     // 16 KiB per A plane per stage
-constexpr int kEpiPatchBytes = 8 * 4096;          // EPI_CORR: transposition patches of the 8 epilogue warps
+constexpr int kEpiPatchBytes = 16 * 2048;         // EPI_GRU_Q: transposition patches of the 16 epilogue warps
 constexpr int kSmemBudget = 227 * 1024 - 2048;
 
 struct alignas(64) TcConvParams {
@@ -55,13 +53,10 @@ struct alignas(64) TcConvParams {
   int n_tiles_n;                  // column tiles (tile id = n_tile * pixel_tiles + pixel_tile)
   int nstages, stage_bytes, tmem_cols;
   int group_chunks;               // K chunks per promotion group (accumulation chain = 12 * group_chunks MMAs)
-  int b_batch_stride;             // B-map coordinate 2 = tap + b * b_batch_stride (correlation: 1, taps = 1)
   int mode, act;
   const float* bias;              // [n_total padded to bn multiple]; may be null
   const float* inv_scale;         // device scalar: 1 / (2^k weight scale); may be null (=1)
   float out_scale;                // applied after the activation (0.25 for the mask head)
-  float corr_div;                 // EPI_CORR: sqrt(C)
-  float corr_mul;                 // EPI_CORR: 1/sqrt(C) when that is an exact power of two (C a power of 4), else 0
   float* out_f32; int f32_stride, f32_c0;
   __half* out_hi; __half* out_lo; int h_stride, h_c0;
   const float* post_scale;        // EPI_LINEAR: optional per-column affine after the bias (folded BatchNorm):
@@ -70,28 +65,11 @@ struct alignas(64) TcConvParams {
   const float* concat_src; int concat_n;   // EPI_LINEAR: fp32 (px, concat_n) appended at columns [n_total, n_total+concat_n)
   float* z; int hid;                       // GRU: z plane (px, hid) fp32
   float* h;                                // GRU: hidden state (px, hid) fp32, updated in place by EPI_GRU_Q
-  int b_stationary;      // 1: all weights of the layer stay resident in shared memory (loaded once per CTA)
-  int b_region_bytes;    // bytes of that resident region (0 otherwise)
   long long* dbg;                          // optional timeline of CTA 0 (tools/timeline.py): [4][512] clock64 stamps
-  // kStats instantiation (encoder norms that need data statistics): the epilogue also reduces each warp's 32 rows to
-  // per-channel (n, mean, M2) partials, part[g][tile * 4 + quarter][{n, mean, M2}][n_total], merged by norm_final_kernel.
-  float* stats_part;
-  int stats_per_image;                     // 1: one statistics group per image (InstanceNorm); 0: one for the batch
-  // kSwap instantiation (narrow layers, cout <= 128): operands exchanged -- the weights are the M operand (TMEM lane ==
-  // output channel, 128 slots, rows past cout_pad zero-filled by TMA) and a 256-pixel tile is the N operand (TMEM column
-  // == pixel).  One 32 KB weight box then serves 256 pixels instead of 128, and the epilogue is coalesced for free: for a
-  // given pixel the 32 lanes of a warp hold 32 consecutive channels.  TH * TW = 256, bn = 256.
-  int swap;
-  int cout;                                // real output channels (swap only)
-  // Programmatic dependent launch (RAFT_B200_PDL=1, experiment): the launch carries the programmatic-serialization
+  // Programmatic dependent launch (default; RAFT_B200_PDL=0 disables): the launch carries the programmatic-serialization
   // attribute, so this grid's CTAs may be scheduled -- and run their prologue -- while the previous kernel in the stream
   // drains; every thread then executes griddepcontrol.wait before touching global memory.
   int pdl;
-  // kTmaStore instantiation of the correlation (RAFT_B200_CORR_TMA_STORE=1, experiment): each warp's transposed 32 x 32
-  // block leaves shared memory through one TMA store of `out_map` (3-D: target pixel, query pixel, batch; 128-byte swizzle)
-  // instead of 8 x 512-byte store instructions; rows / columns past the level's extent are clipped by the TMA unit.
-  int out_tma;
-  CUtensorMap out_map;
   // EPI_LINEAR with n_total == 2 (flow_head.conv2) inside the iteration loop: coords1 += delta_flow and
   // flow = coords1 - coords0 (model.py:102, :97) are applied by the thread that holds the pixel's two output columns.
   float* adv_coords;                       // (px, 2) coords1, updated in place; null = no fused advance
@@ -323,122 +301,28 @@ __device__ __forceinline__ void tc_epilogue_q_t(const TcConvParams& p, float (&v
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Statistics epilogue (kStats): raw convolution output y = acc * inv_scale + bias to the fp32 plane, plus the
-// per-channel (n, mean, M2) of this warp's 32 rows, so that the InstanceNorm / training-BatchNorm statistics need no
-// second pass over y.  Two-pass in registers (mean first, then squared deviations): no E[x^2]-E[x]^2 cancellation.
-// ------------------------------------------------------------------------------------------------
-// Sums t[0..15] over the 32 lanes; afterwards lane L holds the total of element L & 15 (in t[0]).  31 shuffles: one
-// butterfly step on all 16 values, then four steps that each halve the number of live values.  Fixed order: deterministic.
-__device__ __forceinline__ float warp_reduce16(float (&t)[16], int lane) {
-#pragma unroll
-  for (int i = 0; i < 16; ++i) t[i] += __shfl_xor_sync(0xffffffffu, t[i], 16);
-#pragma unroll
-  for (int step = 0; step < 4; ++step) {
-    const int off = 8 >> step, cnt = 8 >> step;
-    const bool up = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < cnt; ++i) {
-      const float send = up ? t[i] : t[i + cnt];
-      const float keep = up ? t[i + cnt] : t[i];
-      t[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-  return t[0];
-}
-
-__device__ __forceinline__ void tc_epilogue_stats(const TcConvParams& p, float (&v)[32], bool valid, size_t pix, int col,
-                                                  float inv_scale, float* __restrict__ part, int lane) {
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const float4 bq = ldg4(p.bias + col + 4 * q);      // bias array is zero-padded past the last column
-    v[4 * q] = v[4 * q] * inv_scale + bq.x; v[4 * q + 1] = v[4 * q + 1] * inv_scale + bq.y;
-    v[4 * q + 2] = v[4 * q + 2] * inv_scale + bq.z; v[4 * q + 3] = v[4 * q + 3] * inv_scale + bq.w;
-  }
-  if (valid && col + 32 <= p.n_total) {                 // host guarantees n_total % 32 == 0 and 16-byte alignment
-    float* dst = p.out_f32 + pix * (size_t)p.f32_stride + p.f32_c0 + col;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) st4(dst + 4 * q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
-  }
-  const float n = (float)__popc(__ballot_sync(0xffffffffu, valid));
-#pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    float t[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) t[j] = valid ? v[half * 16 + j] : 0.0f;
-    const float sum = warp_reduce16(t, lane);
-    const float mean = n > 0.0f ? sum / n : 0.0f;       // lane L: channel col + half*16 + (L & 15)
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float mj = __shfl_sync(0xffffffffu, mean, j);
-      const float d = valid ? v[half * 16 + j] - mj : 0.0f;
-      t[j] = d * d;
-    }
-    const float m2 = warp_reduce16(t, lane);
-    const int c = col + half * 16 + lane;
-    if (lane < 16 && c < p.n_total) {
-      part[c] = n;
-      part[p.n_total + c] = mean;
-      part[2 * p.n_total + c] = m2;
-    }
-  }
-}
-
-// Coalesced store of one 32x32 accumulator block of the correlation volume (patch = swizzled transposition buffer):
-// 8 lanes x 16 bytes cover a row, so a warp writes 4 full 128-byte pyramid rows per instruction.
-__device__ __noinline__ void tc_store_corr_block(const float* patch, long long pix_lane, float* out, int stride, int col0,
-                                                 int ncols_left, int n_total, float corr_mul, float corr_div) {
-  const int lane = threadIdx.x & 31;
-  const int rsub = lane >> 3, q4 = lane & 7;
-  const int col = col0 + 4 * q4;
-#pragma unroll 2
-  for (int i = 0; i < 8; ++i) {
-    const int r = 4 * i + rsub;
-    const long long pl = __shfl_sync(0xffffffffu, pix_lane, r);
-    float4 a4 = *reinterpret_cast<const float4*>(patch + r * 32 + ((q4 ^ (r & 7)) << 2));
-    if (corr_mul != 0.0f) {
-      a4.x *= corr_mul; a4.y *= corr_mul; a4.z *= corr_mul; a4.w *= corr_mul;
-    } else {
-      a4.x = __fdiv_rn(a4.x, corr_div); a4.y = __fdiv_rn(a4.y, corr_div);
-      a4.z = __fdiv_rn(a4.z, corr_div); a4.w = __fdiv_rn(a4.w, corr_div);
-    }
-    if (pl >= 0 && 4 * q4 < ncols_left) {
-      float* dst = out + (size_t)pl * stride + col;
-      if (col + 4 <= n_total && (stride & 3) == 0) {
-        *reinterpret_cast<float4*>(dst) = a4;
-      } else {
-        if (col < n_total) dst[0] = a4.x;
-        if (col + 1 < n_total) dst[1] = a4.y;
-        if (col + 2 < n_total) dst[2] = a4.z;
-        if (col + 3 < n_total) dst[3] = a4.w;
-      }
-    }
-  }
-}
 #endif
 
-// kCorr selects the correlation epilogue at compile time so that its transposition path costs the convolution
-// instantiation neither registers nor code.
-template <bool kCorr, int kEpiWarps, bool kRowEpi, bool kStats = false, bool kSwap = false, bool kTmaStore = false>
-__global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_tc_kernel(const __grid_constant__ TcConvParams p) {
+// kRowEpi selects the epilogue form at compile time: thread-per-row registers (EPI_LINEAR, EPI_GRU_ZR) or transposed through
+// shared-memory patches (EPI_GRU_Q), so that neither costs the other registers or code.
+template <bool kRowEpi>
+__global__ void __launch_bounds__(64 + 32 * kEpiWarpsConv, 1) conv_tc_kernel(const __grid_constant__ TcConvParams p) {
 #if defined(__CUDA_ARCH__)
   // Persistent: CTA c processes output tiles c, c + gridDim.x, ...  A tile is (pixel tile, column tile).  All
   // three roles walk the same tile sequence; the smem ring and the two TMEM buffers carry straight across
   // tile boundaries, so the loads and MMAs of tile i+1 overlap the epilogue of tile i.
+  constexpr int kEpiWarps = kEpiWarpsConv;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nst = p.nstages;
   const int b_bytes = p.bn * kChunkK * 2;
-  uint8_t* bsm = smem;                                        // resident weights (b_stationary), else empty
-  uint8_t* stages = smem + p.b_region_bytes;                  // ring of nst stages
+  uint8_t* stages = smem;                                     // ring of nst stages
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(stages + (size_t)nst * p.stage_bytes);
   uint64_t* empty_bar = full_bar + nst;
   uint64_t* acc_full = empty_bar + nst;      // [2] issuer -> promotion warps
   uint64_t* acc_empty = acc_full + 2;        // [2] promotion warps -> issuer
-  uint64_t* b_full = acc_empty + 2;          // resident weights landed
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(b_full + 1);
-  float* patches = reinterpret_cast<float*>(stages + (size_t)nst * p.stage_bytes + (kTmaStore ? 1024 : 256));   // transposition
-                                             // patches (if any); 1024-byte aligned where a TMA store reads them (swizzle phase)
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* patches = reinterpret_cast<float*>(stages + (size_t)nst * p.stage_bytes + 256);   // transposition patches (GRU q)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -452,7 +336,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_tc_kernel(const _
   const int ngroups = (total + gsz - 1) / gsz;            // promotion groups per tile
   const int nchunks32 = (p.bn + 31) >> 5;                 // 32-column accumulator chunks
   constexpr int kParts = kEpiWarps / 4;                   // warps per TMEM lane quarter: each takes a slice of the columns
-  constexpr int kMaxCh = 8 / kParts;                      // accumulator chunks per thread (2 or 4)
+  constexpr int kMaxCh = 8 / kParts;                      // accumulator chunks per thread (2)
   const int chunks_per_part = (nchunks32 + kParts - 1) / kParts;
 
   if (warp == 0 && lane == 0) {
@@ -464,7 +348,6 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_tc_kernel(const _
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], 4 * ((nchunks32 + chunks_per_part - 1) / chunks_per_part));   // one arrival per participating warp
     }
-    mbar_init(b_full, 1);
     fence_mbar_init();
     prefetch_tmap(&p.a_map[0]);
     prefetch_tmap(&p.b_map);
@@ -494,7 +377,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_tc_kernel(const _
       if (p.pdl) {
         // Convolution weights do not depend on the previous grid: fetch them for the first stages of this CTA's first
         // tile while that grid is still draining, then wait, then fetch the activations.
-        if (!kSwap && !p.b_stationary && p.b_batch_stride == 0 && (int)blockIdx.x < ntiles) {
+        if ((int)blockIdx.x < ntiles) {
           const int n0 = ((int)blockIdx.x / mtiles) * p.bn;
           npre = min(nst, total);
 #pragma unroll 1
@@ -507,15 +390,6 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_tc_kernel(const _
         asm volatile("griddepcontrol.wait;" ::: "memory");
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
       }
-      if (p.b_stationary) {
-        // Measured (tools/tma_probe.cu, timelines): a TMA box costs max(~616 cycles, bytes / 53 B/clk) and boxes are
-        // served one after the other, so for narrow layers (cout 64: a 16 KB weight box per chunk) the weight box
-        // costs as much as the 32 KB activation box.  When all taps of the layer fit, fetch them ONCE per CTA --
-        // one box per 64-channel slice, [plane][tap][cout][64] -- and stream only activations afterwards.
-        mbar_arrive_expect_tx(b_full, (uint32_t)p.b_region_bytes);
-        for (int kc = 0; kc < chunks_per_tap; ++kc)
-          tma_load_4d(bsm + (size_t)kc * 2 * ntaps * b_bytes, &p.b_map, b_full, kc * kChunkK, 0, 0, 0);
-      }
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int nt = t / mtiles;
         int mt = t - nt * mtiles;
@@ -526,7 +400,6 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_tc_kernel(const _
         const int x0 = tx * p.TW * p.stride, y0 = ty * p.TH * p.stride, n0 = nt * p.bn;
         for (int tap = 0; tap < ntaps; ++tap) {
           const int dy = tap / p.kw - p.ph, dx = tap % p.kw - p.pw;
-          const int tcoord = tap + b * p.b_batch_stride;
           int kc = 0;
           for (int seg = 0; seg < p.nseg; ++seg) {
             for (int ch = 0; ch < p.seg_chunks[seg]; ++ch, ++kc, ++it) {
@@ -538,13 +411,8 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_tc_kernel(const _
               if (it >= npre) mbar_arrive_expect_tx(&full_bar[s], (uint32_t)p.stage_bytes);
               const int c = p.seg_c0[seg] + ch * kChunkK;
               // two boxes per stage: [A_hi | A_lo] and [B_hi | B_lo] (TMA cost is per box, not per byte)
-              if constexpr (kSwap) {   // weights -> M-operand slot (128 rows x 2 planes), 256 pixels -> N-operand slot
-                tma_load_4d(st, &p.b_map, &full_bar[s], kc * kChunkK, 0, tcoord, 0);
-                tma_load_5d(st + 2 * kABytes, &p.a_map[seg], &full_bar[s], c, x0 + dx, y0 + dy, b, 0);
-              } else {
-                tma_load_5d(st, &p.a_map[seg], &full_bar[s], c, x0 + dx, y0 + dy, b, 0);
-                if (!p.b_stationary && it >= npre) tma_load_4d(st + 2 * kABytes, &p.b_map, &full_bar[s], kc * kChunkK, n0, tcoord, 0);
-              }
+              tma_load_5d(st, &p.a_map[seg], &full_bar[s], c, x0 + dx, y0 + dy, b, 0);
+              if (it >= npre) tma_load_4d(st + 2 * kABytes, &p.b_map, &full_bar[s], kc * kChunkK, n0, tap, 0);
             }
           }
         }
@@ -554,10 +422,6 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_tc_kernel(const _
     // ===================== MMA issuer =====================
     const uint32_t idesc = make_idesc_f16(kTileM, p.bn);
     int it = 0, gg = 0;
-    if (p.b_stationary) {
-      mbar_wait(b_full, 0u);
-      tc_fence_after();
-    }
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
       int done = 0;
       for (int g = 0; g < ngroups; ++g, ++gg) {
@@ -575,16 +439,10 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_tc_kernel(const _
           if (p.dbg && blockIdx.x == 0 && it < 512 && lane == 0) p.dbg[512 + it] = clock64();   // data landed
           if (elect_one()) {
             const uint32_t sa = smem_u32(stages + (size_t)s * p.stage_bytes);
-            uint32_t sb_hi = sa + 2 * kABytes, sb_lo = sa + 2 * kABytes + b_bytes;
-            if (p.b_stationary) {                            // chunk `done` of the tile = (tap, 64-channel slice kc)
-              const int tap = done / chunks_per_tap, kc = done - tap * chunks_per_tap;
-              sb_hi = smem_u32(bsm) + (uint32_t)((kc * 2 * ntaps + tap) * b_bytes);
-              sb_lo = sb_hi + (uint32_t)(ntaps * b_bytes);
-            }
             const uint64_t a_hi = make_desc_sw128(sa);
             const uint64_t a_lo = make_desc_sw128(sa + kABytes);
-            const uint64_t b_hi = make_desc_sw128(sb_hi);
-            const uint64_t b_lo = make_desc_sw128(sb_lo);
+            const uint64_t b_hi = make_desc_sw128(sa + 2 * kABytes);
+            const uint64_t b_lo = make_desc_sw128(sa + 2 * kABytes + b_bytes);
 #pragma unroll
             for (int k = 0; k < kChunkK / 16; ++k)   // +32 bytes per K=16 step == +2 in 16-byte units
               umma_f16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (!first || k > 0) ? 1u : 0u);
@@ -600,7 +458,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_tc_kernel(const _
       }
     }
   } else {
-    // ===================== promotion + epilogue (warps 2..9) =====================
+    // ===================== promotion + epilogue (warps 2..17) =====================
     const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
     const int part_id = (warp - 2) >> 2;             // column slice of this warp within its lane quarter
     const int chunk0 = part_id * chunks_per_part;
@@ -658,149 +516,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_tc_kernel(const _
         const int ty = mt % p.tiles_y;
         const int b = mt / p.tiles_y;
         const int x = tx * p.TW + xl, y = ty * p.TH + yl;
-        if constexpr (kCorr) {
-          // Pyramid rows are 128 px * N2 * 4 B apart: written thread-per-row, every store instruction touches 32 lines
-          // with 16 bytes each (measured ~20 us per 128 KB tile).  Transpose each 32x32 block through a swizzled smem
-          // patch instead: 8 lanes x 16 bytes cover one row, a warp writes 4 full 128-byte rows per instruction.
-          float* patch = patches + (warp - 2) * 1024;
-          if constexpr (kTmaStore) {
-#pragma unroll
-            for (int ci = 0; ci < kMaxCh; ++ci) {
-              if (ci < my_chunks) {
-                const int c0 = (chunk0 + ci) * 32;
-                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // patch no longer being read
-                __syncwarp();
-#pragma unroll
-                for (int qq = 0; qq < 8; ++qq) {
-                  float4 a4 = make_float4(racc[ci][4 * qq], racc[ci][4 * qq + 1], racc[ci][4 * qq + 2], racc[ci][4 * qq + 3]);
-                  if (p.corr_mul != 0.0f) {
-                    a4.x *= p.corr_mul; a4.y *= p.corr_mul; a4.z *= p.corr_mul; a4.w *= p.corr_mul;
-                  } else {
-                    a4.x = __fdiv_rn(a4.x, p.corr_div); a4.y = __fdiv_rn(a4.y, p.corr_div);
-                    a4.z = __fdiv_rn(a4.z, p.corr_div); a4.w = __fdiv_rn(a4.w, p.corr_div);
-                  }
-                  *reinterpret_cast<float4*>(patch + lane * 32 + ((qq ^ (lane & 7)) << 2)) = a4;
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the TMA unit
-                __syncwarp();
-                const int col0 = nt * p.bn + c0, row0 = tx * p.TW + quarter * 32;
-                if (lane == 0 && col0 < p.n_total && row0 < p.W) {
-                  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
-                                   reinterpret_cast<uint64_t>(&p.out_map)),
-                               "r"(smem_u32(patch)), "r"(col0), "r"(row0), "r"(b)
-                               : "memory");
-                  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                }
-              }
-            }
-          } else {
-          const long long pix_lane = (x < p.W && y < p.H) ? ((long long)b * p.H + y) * p.W + x : -1;
-#pragma unroll
-          for (int ci = 0; ci < kMaxCh; ++ci) {
-            if (ci < my_chunks) {
-              const int c0 = (chunk0 + ci) * 32;
-              __syncwarp();
-#pragma unroll
-              for (int qq = 0; qq < 8; ++qq)
-                *reinterpret_cast<float4*>(patch + lane * 32 + ((qq ^ (lane & 7)) << 2)) =
-                    make_float4(racc[ci][4 * qq], racc[ci][4 * qq + 1], racc[ci][4 * qq + 2], racc[ci][4 * qq + 3]);
-              __syncwarp();
-              tc_store_corr_block(patch, pix_lane, p.out_f32, p.f32_stride, nt * p.bn + c0, p.bn - c0, p.n_total, p.corr_mul,
-                                  p.corr_div);
-            }
-          }
-          }
-        } else if constexpr (kSwap) {      // operands exchanged: this thread = output channel m, columns = 256 pixels
-          const int ch = m;
-          const bool ch_ok = ch < p.cout;
-          const float bias = (ch_ok && p.bias) ? __ldg(p.bias + ch) : 0.0f;
-          const int tshift = 31 - __clz(p.TW);                         // TW is a power of two
-          const int px0 = tx * p.TW, py0 = ty * p.TH;
-#pragma unroll
-          for (int ci = 0; ci < kMaxCh; ++ci)
-#pragma unroll
-            for (int j = 0; j < 32; ++j) racc[ci][j] = racc[ci][j] * inv_scale + bias;
-          if (p.stats_part) {
-            // raw output + this channel's (n, mean, M2) over the warp-slice's 64 pixels: two passes over registers
-            float n = 0.0f, sum = 0.0f;
-#pragma unroll
-            for (int ci = 0; ci < kMaxCh; ++ci) {
-              if (ci < my_chunks) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  const int mm = (chunk0 + ci) * 32 + j;
-                  const int xx = px0 + (mm & (p.TW - 1)), yy = py0 + (mm >> tshift);
-                  if (xx < p.W && yy < p.H) {
-                    n += 1.0f;
-                    sum += racc[ci][j];
-                    if (ch_ok) p.out_f32[(((size_t)b * p.H + yy) * p.W + xx) * p.f32_stride + p.f32_c0 + ch] = racc[ci][j];
-                  }
-                }
-              }
-            }
-            const float mean = n > 0.0f ? sum / n : 0.0f;
-            float m2 = 0.0f;
-#pragma unroll
-            for (int ci = 0; ci < kMaxCh; ++ci) {
-              if (ci < my_chunks) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  const int mm = (chunk0 + ci) * 32 + j;
-                  const int xx = px0 + (mm & (p.TW - 1)), yy = py0 + (mm >> tshift);
-                  const float d = racc[ci][j] - mean;
-                  if (xx < p.W && yy < p.H) m2 += d * d;
-                }
-              }
-            }
-            if (ch_ok) {
-              const int tiles_img = p.tiles_y * p.tiles_x;
-              const int nsplit = (p.stats_per_image ? tiles_img : p.B * tiles_img) * 4;
-              const int tile_local = (p.stats_per_image ? 0 : b * tiles_img) + ty * p.tiles_x + tx;
-              float* part = p.stats_part + ((size_t)(p.stats_per_image ? b : 0) * nsplit + tile_local * 4 + part_id) * 3 * p.cout;
-              part[ch] = n;
-              part[p.cout + ch] = mean;
-              part[2 * p.cout + ch] = m2;
-            }
-          } else if (ch_ok) {
-            const float psc = p.post_scale ? __ldg(p.post_scale + ch) : 1.0f;
-            const float psh = p.post_scale ? __ldg(p.post_shift + ch) : 0.0f;
-#pragma unroll
-            for (int ci = 0; ci < kMaxCh; ++ci) {
-              if (ci < my_chunks) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  const int mm = (chunk0 + ci) * 32 + j;
-                  const int xx = px0 + (mm & (p.TW - 1)), yy = py0 + (mm >> tshift);
-                  if (xx < p.W && yy < p.H) {
-                    const size_t pix = ((size_t)b * p.H + yy) * p.W + xx;
-                    float v = racc[ci][j] * psc + psh;
-                    if (p.act == ACT_RELU) v = fmaxf(v, 0.0f);
-                    v *= p.out_scale;
-                    if (p.residual) v = fmaxf(v + __ldg(p.residual + pix * (size_t)p.res_stride + p.res_c0 + ch), 0.0f);
-                    if (p.out_f32) p.out_f32[pix * (size_t)p.f32_stride + p.f32_c0 + ch] = v;
-                    if (p.out_hi) {
-                      __half hh, ll;
-                      split_f16(v, hh, ll);
-                      p.out_hi[pix * (size_t)p.h_stride + p.h_c0 + ch] = hh;
-                      p.out_lo[pix * (size_t)p.h_stride + p.h_c0 + ch] = ll;
-                    }
-                  }
-                }
-              }
-            }
-          }
-        } else if constexpr (kStats) {     // raw output + statistics partials (see tc_epilogue_stats)
-          const bool valid = x < p.W && y < p.H;
-          const size_t pix = valid ? ((size_t)b * p.H + y) * p.W + x : 0;
-          const int tiles_img = p.tiles_y * p.tiles_x;
-          const int nsplit = (p.stats_per_image ? tiles_img : p.B * tiles_img) * 4;
-          const int tile_local = (p.stats_per_image ? 0 : b * tiles_img) + ty * p.tiles_x + tx;
-          float* part = p.stats_part + ((size_t)(p.stats_per_image ? b : 0) * nsplit + tile_local * 4 + quarter) * 3 * p.n_total;
-#pragma unroll
-          for (int ci = 0; ci < kMaxCh; ++ci) {
-            if (ci < my_chunks) tc_epilogue_stats(p, racc[ci], valid, pix, nt * p.bn + (chunk0 + ci) * 32, inv_scale, part, lane);
-          }
-        } else if constexpr (kRowEpi) {    // convolution, thread-per-row register epilogue (EPI_LINEAR, EPI_GRU_ZR)
+        if constexpr (kRowEpi) {    // thread-per-row register epilogue (EPI_LINEAR, EPI_GRU_ZR)
           if (x < p.W && y < p.H) {
             const size_t pix = ((size_t)b * p.H + y) * p.W + x;
 #pragma unroll
@@ -857,9 +573,6 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_tc_kernel(const _
     }
   }
 
-  if constexpr (kTmaStore) {
-    if (warp >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // this thread's bulk stores are complete
-  }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
@@ -869,7 +582,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) conv_tc_kernel(const _
 // ------------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------------
-inline bool tc_uses_patch(int mode) { return mode == EPI_CORR || mode == EPI_GRU_Q; }
+inline bool tc_uses_patch(int mode) { return mode == EPI_GRU_Q; }
 
 inline void tc_pick_tile(int W, int H, int* tw, int* th) {
   // TW*TH = 128 with TW a power of two; minimise padded area, prefer wide tiles on ties.
@@ -885,71 +598,32 @@ inline void tc_pick_tile(int W, int H, int* tw, int* th) {
   }
 }
 
-// 256-pixel tile of the kSwap instantiation: TW a power of two, TW * TH = 256, both box extents (x stride) <= 256.
-inline bool tc_pick_tile256(int W, int H, int stride, int* tw, int* th) {
-  long best = -1;
-  for (int t = 256; t >= 1; t >>= 1) {
-    const int hh = 256 / t;
-    if (t * stride > 256 || hh * stride > 256) continue;
-    const long area = (long)round_up(W, t) * round_up(H, hh);
-    if (best < 0 || area < best) {
-      best = area;
-      *tw = t;
-      *th = hh;
-    }
-  }
-  return best >= 0;
-}
-
 // Fills the derived launch fields (tile grid, stages, TMEM columns) of `p`; returns bytes of
 // dynamic shared memory.  Caller has set bn, B, H, W, TH, TW.
 inline int tc_finalize(TcConvParams& p) {
   p.tiles_x = ceil_div(p.W, p.TW);
   p.tiles_y = ceil_div(p.H, p.TH);
   p.stage_bytes = 2 * kABytes + 2 * p.bn * kChunkK * 2;
-  if (p.b_stationary) p.stage_bytes = 2 * kABytes;       // weights live in the resident region, stages carry activations only
-  else p.b_region_bytes = 0;
-  const int patch = tc_uses_patch(p.mode) ? kEpiPatchBytes : 0;   // 8 x 4 KB (correlation) or 16 x 2 KB (GRU q) patches
-  int nst = (kSmemBudget - patch - p.b_region_bytes - (p.out_tma ? 768 : 0)) / p.stage_bytes;
+  const int patch = tc_uses_patch(p.mode) ? kEpiPatchBytes : 0;   // 16 x 2 KB patches (GRU q)
+  int nst = (kSmemBudget - patch) / p.stage_bytes;
   if (nst > 8) nst = 8;
   p.nstages = nst;
   int cols = 32;
   while (cols < 2 * p.bn) cols <<= 1;           // two accumulator buffers (ping-pong promotion)
   p.tmem_cols = cols;
   if (p.group_chunks <= 0) p.group_chunks = 2;
-  return p.b_region_bytes + nst * p.stage_bytes + 1024 /*align slack*/ + (p.out_tma ? 1024 : 256) /*barriers*/ + patch;
+  return nst * p.stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + patch;
 }
 
-// Resident-weights plan for a stride-any LINEAR convolution whose whole weight set fits beside >= 2 activation stages
-// and whose CTAs each process several tiles (otherwise streaming moves the same bytes).  Rebuilds p.b_map with a box
-// that spans all taps.  RAFT_B200_BSTAT=0 disables it (A/B timing), =2 forces it for small inputs (tests).  Call after bn, B, H, W, TH, TW, kh, kw, nseg,
-// seg_chunks are set and before tc_launch().
-inline int tc_try_stationary(TcConvParams& p, const __half* w_hi, const __half* w_lo, int cout_pad, int cin_pad) {
-  static const int enabled = [] { const char* e = getenv("RAFT_B200_BSTAT"); return e ? atoi(e) : 0; }();   // default off (measured slower); 1: on, 2: also for few tiles
-  p.b_stationary = 0;
-  p.b_region_bytes = 0;
-  if (!enabled || p.mode != EPI_LINEAR || p.nseg != 1 || p.bn != cout_pad || p.b_batch_stride != 0) return RAFT_OK;
-  const int taps = p.kh * p.kw, chunks = p.seg_chunks[0];
-  if (taps > 256 || chunks * kChunkK != cin_pad) return RAFT_OK;
-  const long bytes = (long)taps * chunks * 2 * p.bn * kChunkK * 2;
-  if (bytes > kSmemBudget - 2 * (2 * kABytes) || bytes >= (1 << 20)) return RAFT_OK;
-  const long mtiles = (long)p.B * ceil_div(p.H, p.TH) * ceil_div(p.W, p.TW);
-  if (mtiles < 2L * kNumSMs && enabled != 2) return RAFT_OK;
-  const ptrdiff_t pstride = reinterpret_cast<const char*>(w_lo) - reinterpret_cast<const char*>(w_hi);
-  if (pstride <= 0 || (pstride & 15)) return RAFT_ERR_BAD_ARG;
-  uint64_t dims[4] = {(uint64_t)cin_pad, (uint64_t)cout_pad, (uint64_t)taps, 2};
-  uint64_t str[3] = {(uint64_t)cin_pad * 2, (uint64_t)cout_pad * cin_pad * 2, (uint64_t)pstride};
-  uint32_t box[4] = {64, (uint32_t)p.bn, (uint32_t)taps, 2};
-  RAFT_TRY(make_tmap_f16(&p.b_map, w_hi, 4, dims, str, box));
-  p.b_stationary = 1;
-  p.b_region_bytes = (int)bytes;
-  return RAFT_OK;
+// RAFT_B200_PDL=0 disables programmatic dependent launch of the per-layer kernel (A/B timing).
+inline bool tc_pdl_enabled() {
+  static const int pdl = [] { const char* e = getenv("RAFT_B200_PDL"); return e ? atoi(e) : 1; }();
+  return pdl != 0;
 }
 
 inline int tc_launch(TcConvParams& p, int n_tiles_n, cudaStream_t stream) {
-  if (p.bn % 16 != 0 || p.bn < 16 || p.bn > 256 || p.TW * p.TH != (p.swap ? 256 : kTileM)) return RAFT_ERR_BAD_SHAPE;
-  if (p.swap && (p.bn != 256 || p.mode != EPI_LINEAR || n_tiles_n != 1 || p.cout < 1 || p.cout > kTileM || (p.TW & (p.TW - 1))))
-    return RAFT_ERR_UNSUPPORTED;
+  if (p.bn % 16 != 0 || p.bn < 16 || p.bn > 256 || p.TW * p.TH != kTileM) return RAFT_ERR_BAD_SHAPE;
+  if (p.mode != EPI_LINEAR && p.mode != EPI_GRU_ZR && p.mode != EPI_GRU_Q) return RAFT_ERR_UNSUPPORTED;
   if (p.stride < 1) p.stride = 1;
   const int smem = tc_finalize(p);
   if (p.nstages < 2) return RAFT_ERR_UNSUPPORTED;
@@ -958,46 +632,21 @@ inline int tc_launch(TcConvParams& p, int n_tiles_n, cudaStream_t stream) {
   RAFT_CUDA_TRY(cudaGetDevice(&dev));
   const unsigned long long dev_bit = 1ull << (dev & 63);
   static unsigned long long attr_set_mask = 0;
-  const bool attr_set = (attr_set_mask & dev_bit) != 0;
-  if (!attr_set) {
-    RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<false, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<false, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<true, kEpiWarpsCorr, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  if (!(attr_set_mask & dev_bit)) {
+    RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set_mask |= dev_bit;
-  }
-  if (p.stats_part || p.swap || p.out_tma) {       // experiment instantiations: configured only when one is selected
-    static unsigned long long attr_set_x_mask = 0;
-    if (!(attr_set_x_mask & dev_bit)) {
-      RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<false, 16, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<false, 16, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<true, kEpiWarpsCorr, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      attr_set_x_mask |= dev_bit;
-    }
   }
   const int mtiles = p.B * p.tiles_y * p.tiles_x;
   p.n_tiles_n = n_tiles_n;
   const long ntiles = (long)mtiles * n_tiles_n;
   const unsigned grid = (unsigned)(ntiles < kNumSMs ? ntiles : kNumSMs);   // one persistent CTA per SM
-  static const int pdl = [] { const char* e = getenv("RAFT_B200_PDL"); return e ? atoi(e) : 0; }();
-  p.pdl = pdl ? 1 : 0;
-  if (p.stats_part && !p.swap &&
-      (p.mode != EPI_LINEAR || p.n_total % 32 != 0 || n_tiles_n != 1 || !p.out_f32 || ((p.f32_stride | p.f32_c0) & 3) || !p.bias))
-    return RAFT_ERR_UNSUPPORTED;
-  const int threads = 64 + 32 * (p.mode == EPI_CORR ? kEpiWarpsCorr : kEpiWarpsConv);
+  p.pdl = tc_pdl_enabled() ? 1 : 0;
+  const int threads = 64 + 32 * kEpiWarpsConv;
+  void (*kern)(TcConvParams) = p.mode == EPI_GRU_Q ? conv_tc_kernel<false> : conv_tc_kernel<true>;
   if (!p.pdl) {
-    if (p.mode == EPI_CORR && p.out_tma) conv_tc_kernel<true, kEpiWarpsCorr, false, false, false, true><<<grid, threads, smem, stream>>>(p);
-    else if (p.mode == EPI_CORR) conv_tc_kernel<true, kEpiWarpsCorr, false><<<grid, threads, smem, stream>>>(p);
-    else if (p.mode == EPI_GRU_Q) conv_tc_kernel<false, kEpiWarpsConv, false><<<grid, threads, smem, stream>>>(p);
-    else if (p.swap) conv_tc_kernel<false, kEpiWarpsConv, true, false, true><<<grid, threads, smem, stream>>>(p);
-    else if (p.stats_part) conv_tc_kernel<false, kEpiWarpsConv, true, true><<<grid, threads, smem, stream>>>(p);
-    else conv_tc_kernel<false, kEpiWarpsConv, true><<<grid, threads, smem, stream>>>(p);
-  } else {                                           // experiment: same kernels with the programmatic-serialization attribute
-    void (*kern)(TcConvParams) = conv_tc_kernel<false, kEpiWarpsConv, true>;
-    if (p.mode == EPI_CORR && p.out_tma) kern = conv_tc_kernel<true, kEpiWarpsCorr, false, false, false, true>;
-    else if (p.mode == EPI_CORR) kern = conv_tc_kernel<true, kEpiWarpsCorr, false>;
-    else if (p.mode == EPI_GRU_Q) kern = conv_tc_kernel<false, kEpiWarpsConv, false>;
-    else if (p.swap) kern = conv_tc_kernel<false, kEpiWarpsConv, true, false, true>;
-    else if (p.stats_part) kern = conv_tc_kernel<false, kEpiWarpsConv, true, true>;
+    kern<<<grid, threads, smem, stream>>>(p);
+  } else {                                             // programmatic-serialization attribute: see the kernel prologue
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid);

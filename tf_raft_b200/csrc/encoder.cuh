@@ -81,7 +81,6 @@ struct EncWs {
   float *X32, *O32, *Y32, *D32;
   __half *Xh, *Xl, *Oh, *Ol, *Fh, *Fl, *Ih, *Il;
   float *part, *mean, *mult;
-  float* part_tiles;     // fused statistics: (n, mean, M2) per (tile, TMEM lane quarter, channel), see conv_tc.cuh kStats
   size_t total;
 };
 constexpr int kNormSplit = 64;
@@ -110,18 +109,6 @@ inline EncWs enc_ws_layout(void* base, int variant, int N, int H, int W) {
     E.Ih = (__half*)take(np1 * 192 * 2); E.Il = (__half*)take(np1 * 192 * 2);
   }
   E.part = (float*)take((size_t)N * kNormSplit * 3 * 256 * 4);
-  {
-    // any 128-pixel tile shape covers an h x w plane with at most h*w/128 + h + w + 1 tiles
-    size_t cap = 0;
-    for (int l = 0; l < 3; ++l) {
-      const int d = 2 << l;
-      const size_t hl = (H + d - 1) / d, wl = (W + d - 1) / d;
-      const int c = l == 0 ? (S.c0 > S.c[0] ? S.c0 : S.c[0]) : S.c[l];
-      const size_t need = (size_t)N * (hl * wl / 128 + hl + wl + 1) * 4 * 3 * c;
-      if (need > cap) cap = need;
-    }
-    E.part_tiles = (float*)take(cap * 4);
-  }
   E.mean = (float*)take((size_t)N * 256 * 4);
   E.mult = (float*)take((size_t)N * 256 * 4);
   E.total = off;
@@ -201,19 +188,11 @@ struct EncCtx {
   const uint8_t* prep; EncLayout L; EncWs W; cudaStream_t st;
   int N, norm_type, stats;    // stats: 1 = statistics from the data (instance, or batch in training)
   int per_image;              // instance: one group per image; batch-training: one group
-  mutable int fused_nsplit;   // > 0: the last enc_conv_tc wrote this many statistics partials per group (fused statistics)
 };
 
-// Statistics of the encoder norms are either a separate pass over y (norm_stats_kernel) or -- RAFT_B200_FUSED_STATS=1,
-// parity-tested on hardware but not yet timed, default off -- partials written by the producing convolution's epilogue.
-inline bool enc_fused_stats() {
-  static const int v = [] { const char* e = getenv("RAFT_B200_FUSED_STATS"); return e ? atoi(e) : 0; }();
-  return v != 0;
-}
-
-// y (npix, C) raw conv output -> normalised, activated, (+skip), re-split.
-// c.fused_nsplit > 0: c.W.part_tiles already holds that many partials per statistics group, written by the
-// enc_conv_tc call that produced y.
+// y (npix, C) raw conv output -> normalised, activated, (+skip), re-split.  (Statistics partials from the convolution
+// epilogue and operand-swapped narrow layers were built and measured in round 2 -- both slower than this form
+// (profiles/README.md) -- and removed.)
 inline int enc_norm_apply(const EncCtx& c, const EncNormSlot& ns, const float* y, size_t npix, int P, int relu,
                           const float* skip32, const __half* skip_hi, const __half* skip_lo, float* out32, __half* hi,
                           __half* lo) {
@@ -221,16 +200,11 @@ inline int enc_norm_apply(const EncCtx& c, const EncNormSlot& ns, const float* y
   const int Pg = c.per_image ? P : (int)npix;
   const float* gamma = reinterpret_cast<const float*>(c.prep + ns.gamma);
   const float* beta = reinterpret_cast<const float*>(c.prep + ns.beta);
-  const bool fused = c.fused_nsplit > 0;
-  if (fused) {
-    norm_final_kernel<<<ceil_div(G * C * 32, 256), 256, 0, c.st>>>(c.W.part_tiles, G, C, c.fused_nsplit, gamma, 1e-3f, c.W.mean, c.W.mult);
-  } else {
-    norm_stats_kernel<<<dim3((unsigned)G, kNormSplit), 256, 0, c.st>>>(y, Pg, C, kNormSplit, c.W.part);
-    norm_final_kernel<<<ceil_div(G * C * 32, 256), 256, 0, c.st>>>(c.W.part, G, C, kNormSplit, gamma, 1e-3f, c.W.mean, c.W.mult);
-  }
+  norm_stats_kernel<<<dim3((unsigned)G, kNormSplit), 256, 0, c.st>>>(y, Pg, C, kNormSplit, c.W.part);
+  norm_final_kernel<<<ceil_div(G * C * 32, 256), 256, 0, c.st>>>(c.W.part, G, C, kNormSplit, gamma, 1e-3f, c.W.mean, c.W.mult);
   norm_apply_kernel<<<grid_for(npix * (pad64(C) / 8)), 256, 0, c.st>>>(y, npix, P, C, c.per_image, c.W.mean, c.W.mult, beta, relu,
                                                                  skip32, skip_hi, skip_lo, out32, hi, lo, pad64(C));
-  g_launches += fused ? 2 : 3;
+  g_launches += 3;
   return raft_launch_status();
 }
 
@@ -241,26 +215,13 @@ inline int enc_conv_tc(const EncCtx& c, const EncConvSlot& cs, const EncNormSlot
                        __half* ohi, __half* olo) {
   TcConvParams p;
   memset(&p, 0, sizeof(p));
-  c.fused_nsplit = 0;
   int tw, th;
   tc_pick_tile(Wout, Hout, &tw, &th);
   if (tw * stride > 256) tw = 128 / stride, th = 128 / tw;
-  // Narrow layers (cout <= 128) with many tiles: exchange the operands (conv_tc.cuh kSwap) so that one weight box serves a
-  // 256-pixel tile.  RAFT_B200_ENC_SWAP=1 (2: regardless of the tile count, for small test inputs); default off -- compiled,
-  // not yet run on hardware.
-  bool swap = false;
-  {
-    static const int flag = [] { const char* e = getenv("RAFT_B200_ENC_SWAP"); return e ? atoi(e) : 0; }();
-    int tw2, th2;
-    if (flag && cs.cout <= kTileM && tc_pick_tile256(Wout, Hout, stride, &tw2, &th2)) {
-      const long mt2 = (long)c.N * ceil_div(Hout, th2) * ceil_div(Wout, tw2);
-      if (flag == 2 || mt2 >= 2L * kNumSMs) { swap = true; tw = tw2; th = th2; }
-    }
-  }
   RAFT_TRY(make_tmap_act2(&p.a_map[0], ahi, alo, c.N, Hin, Win, cs.cin_pad, tw, th, stride));
   RAFT_TRY(make_tmap_wgt2(&p.b_map, reinterpret_cast<const __half*>(c.prep + cs.hi),
                           reinterpret_cast<const __half*>(c.prep + cs.lo), cs.kh * cs.kw, cs.cout_pad, cs.cin_pad,
-                          swap ? kTileM : cs.cout_pad));
+                          cs.cout_pad));
   p.nseg = 1; p.seg_chunks[0] = cs.cin_pad / kChunkK; p.seg_c0[0] = 0;
   p.kh = cs.kh; p.kw = cs.kw; p.stride = stride;
   // Keras 'same': stride 1 -> (k-1)/2 before; stride 2 on even input -> total k-2, before = (k-2)/2 (0 for 3x3);
@@ -272,7 +233,6 @@ inline int enc_conv_tc(const EncCtx& c, const EncConvSlot& cs, const EncNormSlot
   }
   p.B = c.N; p.H = Hout; p.W = Wout; p.TH = th; p.TW = tw;
   p.bn = cs.cout_pad; p.n_total = cs.cout;
-  if (swap) { p.swap = 1; p.cout = cs.cout; p.bn = 256; p.n_total = 256; }
   p.mode = EPI_LINEAR; p.out_scale = 1.0f;
   p.bias = reinterpret_cast<const float*>(c.prep + cs.bias);
   p.inv_scale = reinterpret_cast<const float*>(c.prep + cs.scale) + 1;
@@ -288,12 +248,6 @@ inline int enc_conv_tc(const EncCtx& c, const EncConvSlot& cs, const EncNormSlot
     p.residual = skip; p.res_stride = cs.cout; p.res_c0 = 0;
   } else {
     p.act = ACT_NONE; p.out_hi = nullptr; p.out_lo = nullptr;
-    if (enc_fused_stats() && (swap || cs.cout % 32 == 0)) {   // statistics partials from this convolution's epilogue
-      p.stats_part = c.W.part_tiles;
-      p.stats_per_image = c.per_image ? 1 : 0;
-      const int tiles = ceil_div(Hout, th) * ceil_div(Wout, tw);
-      c.fused_nsplit = (c.per_image ? tiles : c.N * tiles) * 4;
-    }
   }
   if (g_dbg_layer >= 1000 && g_dbg_count++ == g_dbg_layer - 1000) p.dbg = g_dbg_buf;   // timeline of the k-th encoder conv
   {
@@ -303,8 +257,6 @@ inline int enc_conv_tc(const EncCtx& c, const EncConvSlot& cs, const EncNormSlot
     static const int grp = [] { const char* e = getenv("RAFT_B200_ENC_GROUP"); return e ? atoi(e) : 5; }();
     if (grp > 0) p.group_chunks = grp;
   }
-  RAFT_TRY(tc_try_stationary(p, reinterpret_cast<const __half*>(c.prep + cs.hi), reinterpret_cast<const __half*>(c.prep + cs.lo),
-                             cs.cout_pad, cs.cin_pad));
   ++g_launches;
   return tc_launch(p, 1, c.st);
 }

@@ -200,87 +200,6 @@ __global__ void __launch_bounds__(256) corr_lookup_kernel(const LookupParams p) 
 }
 
 // ------------------------------------------------------------------------------------------------
-// flow_head.conv2 (update.py:11,14): 3x3 'same' convolution, C hidden channels -> the 2 flow-delta channels, read from
-// the fp16 hi/lo operand planes of the hidden activation, fp32 FFMA accumulation (experiment, RAFT_B200_FH2_SIMT=1).
-// On the tensor-core path this layer is a 16-column GEMM that moves a full 128 x C activation tile per tap for two useful
-// output columns (22.6 us of TMA time, measured 32 us); here one block owns an 8 x 16 pixel tile, stages the 10 x 18 halo
-// of 32 channels at a time in shared memory (row pitch 36 floats: conflict-free 16-byte reads) and every thread
-// accumulates its own pixel.  Fixed summation order: deterministic.
-// ------------------------------------------------------------------------------------------------
-struct FlowHead2Params {
-  const __half* hi; const __half* lo;   // hidden activation planes, (B*H*W, cstride), channels [c0, c0 + C)
-  int cstride, c0, C;                   // C % 32 == 0
-  const float* w;                       // HWIO (3, 3, C, 2) fp32
-  const float* bias;                    // (2)
-  float* delta;                         // (B*H*W, 2)
-  int B, H, W;
-};
-__global__ void __launch_bounds__(128) flow_head2_kernel(const FlowHead2Params p) {
-  constexpr int TH = 8, TW = 16, HH = TH + 2, HW = TW + 2, SLAB = 32, PITCH = SLAB + 4;
-  __shared__ __align__(16) float act[HH * HW * PITCH];      // 25,920 B
-  __shared__ __align__(16) float wsm[9 * SLAB * 2];         //  2,304 B: [tap][channel][out]
-  const int tiles_x = (p.W + TW - 1) / TW, tiles_y = (p.H + TH - 1) / TH;
-  int t = blockIdx.x;
-  const int tx = t % tiles_x; t /= tiles_x;
-  const int ty = t % tiles_y;
-  const int b = t / tiles_y;
-  const int x0 = tx * TW - 1, y0 = ty * TH - 1;             // halo origin
-  const int py = threadIdx.x / TW, px = threadIdx.x % TW;
-  float acc0 = 0.0f, acc1 = 0.0f;
-  for (int cs = 0; cs < p.C; cs += SLAB) {
-    __syncthreads();                                        // previous slab fully consumed
-    // stage the halo: 8 channels (16 bytes of each plane) per load, hi + lo summed to fp32
-    for (int i = threadIdx.x; i < HH * HW * (SLAB / 8); i += blockDim.x) {
-      const int g = i % (SLAB / 8), hp = i / (SLAB / 8);
-      const int hx = hp % HW, hy = hp / HW;
-      const int x = x0 + hx, y = y0 + hy;
-      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      if (x >= 0 && x < p.W && y >= 0 && y < p.H) {
-        const size_t o = (((size_t)b * p.H + y) * p.W + x) * p.cstride + p.c0 + cs + g * 8;
-        const uint4 h4 = *reinterpret_cast<const uint4*>(p.hi + o), l4 = *reinterpret_cast<const uint4*>(p.lo + o);
-        const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
-          const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[e]));
-          v[2 * e] = hf.x + lf.x;
-          v[2 * e + 1] = hf.y + lf.y;
-        }
-      }
-      float* dst = act + hp * PITCH + g * 8;
-      *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-      *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
-    }
-    for (int i = threadIdx.x; i < 9 * SLAB * 2; i += blockDim.x) {
-      const int o = i & 1, c = (i >> 1) % SLAB, tap = (i >> 1) / SLAB;
-      wsm[i] = __ldg(p.w + ((size_t)tap * p.C + cs + c) * 2 + o);
-    }
-    __syncthreads();
-#pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-      const float* a = act + ((py + tap / 3) * HW + px + tap % 3) * PITCH;
-      const float* wt = wsm + tap * SLAB * 2;
-#pragma unroll
-      for (int c4 = 0; c4 < SLAB / 4; ++c4) {
-        const float4 av = *reinterpret_cast<const float4*>(a + 4 * c4);
-        const float4 w01 = *reinterpret_cast<const float4*>(wt + 8 * c4);       // (c, o): (0,0) (0,1) (1,0) (1,1)
-        const float4 w23 = *reinterpret_cast<const float4*>(wt + 8 * c4 + 4);   //         (2,0) (2,1) (3,0) (3,1)
-        acc0 = fmaf(av.x, w01.x, acc0); acc1 = fmaf(av.x, w01.y, acc1);
-        acc0 = fmaf(av.y, w01.z, acc0); acc1 = fmaf(av.y, w01.w, acc1);
-        acc0 = fmaf(av.z, w23.x, acc0); acc1 = fmaf(av.z, w23.y, acc1);
-        acc0 = fmaf(av.w, w23.z, acc0); acc1 = fmaf(av.w, w23.w, acc1);
-      }
-    }
-  }
-  const int x = tx * TW + px, y = ty * TH + py;
-  if (x < p.W && y < p.H) {
-    float* d = p.delta + (((size_t)b * p.H + y) * p.W + x) * 2;
-    d[0] = acc0 + __ldg(p.bias);
-    d[1] = acc1 + __ldg(p.bias + 1);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
 // fp32 correlation (RAFT_PREC_FP32): out[b, q, n] = <f1[b,q,:], f2[b,n,:]> / sqrt(C)  (corr.py:154-162)
 // 64x64 tile, 16-wide K slab, 4x4 micro-tile per thread.
 // ------------------------------------------------------------------------------------------------

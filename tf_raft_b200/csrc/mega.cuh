@@ -370,7 +370,6 @@ inline int mega_add(MegaPlan& M, int layer_id, TcConvParams& p, int n_tiles_n, c
   if (p.bn % 16 != 0 || p.bn < 16 || p.bn > 256 || p.TW * p.TH != kTileM) return RAFT_ERR_BAD_SHAPE;
   if (p.mode != EPI_LINEAR && p.mode != EPI_GRU_ZR && p.mode != EPI_GRU_Q) return RAFT_ERR_UNSUPPORTED;
   if (p.stride < 1) p.stride = 1;
-  p.b_stationary = 0;
   const int saved_mode = p.mode;
   p.mode = EPI_GRU_Q;                      // reserve the transposition patches whatever the layer's mode (one smem layout)
   tc_finalize(p);

@@ -71,18 +71,4 @@ inline int make_tmap_wgt2(CUtensorMap* out, const __half* hi, const __half* lo, 
   return make_tmap_f16(out, hi, 4, dims, str, box);
 }
 
-// Output map of one correlation-pyramid level for TMA stores: fp32 (N2 target pixels, N query pixels, B), box {32, 32, 1},
-// 128-byte swizzle (matches the transposition patch of conv_tc_kernel).  Needs N2 % 4 == 0 (16-byte row stride).
-inline int make_tmap_corr_out(CUtensorMap* out, float* base, int B, int N, int N2) {
-  EncodeTiledFn fn = encode_tiled_fn();
-  if (!fn) return RAFT_ERR_DRIVER;
-  if (N2 % 4 != 0 || (reinterpret_cast<uintptr_t>(base) & 15)) return RAFT_ERR_BAD_SHAPE;
-  cuuint64_t gdim[3] = {(cuuint64_t)N2, (cuuint64_t)N, (cuuint64_t)B};
-  cuuint64_t gstr[2] = {(cuuint64_t)N2 * 4, (cuuint64_t)N * N2 * 4};
-  cuuint32_t bx[3] = {32, 32, 1}, es[3] = {1, 1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : RAFT_ERR_DRIVER;
-}
-
 }  // namespace raft

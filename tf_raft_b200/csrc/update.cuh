@@ -277,7 +277,6 @@ inline int launch_tc_layer(const UpdateCtx& c, int layer, int nseg, const TcSeg*
   p.kh = L.kh; p.kw = L.kw; p.ph = (L.kh - 1) / 2; p.pw = (L.kw - 1) / 2;
   p.B = c.B; p.H = c.h; p.W = c.w; p.TH = th; p.TW = tw;
   p.bn = L.bn;
-  p.b_batch_stride = 0;
   p.bias = reinterpret_cast<const float*>(c.prepared + c.PL.tc_bias[layer]);
   p.inv_scale = reinterpret_cast<const float*>(c.prepared + c.PL.tc_scale[layer]) + 1;
   if (p.out_scale == 0.0f) p.out_scale = 1.0f;

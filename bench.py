@@ -279,7 +279,7 @@ def run_ours(args, cfg):
             t0 = time.perf_counter()
             n = 0
             for out in parallel.predict_stream(lambda a, b: model.predict_step((a, b)),
-                                               (host[i % n_rot] for i in range(steps)), device):
+                                               (host[i % n_rot] for i in range(steps)), device, reuse_host_buffers=True):
                 n += out.shape[0]
             torch.cuda.synchronize()
             wall = time.perf_counter() - t0

@@ -32,7 +32,7 @@ def main():
     raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
-    print(f'# ncu --set full --clock-control none  (gpurun, B200, round 1) -- selected metrics per launch; source report: {rep}')
+    print(f'# ncu --set full --clock-control none  (gpurun, B200) -- selected metrics per launch; source report: {rep}')
     for name in KEEP:
         if name not in hdr:
             continue

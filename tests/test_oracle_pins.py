@@ -84,3 +84,24 @@ def test_model_output_contract():
         assert len(preds) == 2
         for f in preds:
             assert tuple(f.shape) == (1, 64, 96, 2)
+
+
+def test_end_point_error_metric_class_known_answer():
+    """reference tests/losses/test_losses.py:70-95 on the product's EndPointError metric (losses.py:46-85)."""
+    import torch
+    from tf_raft_b200.losses import EndPointError
+    flow_gt = (np.array([[[0, 1], [0, 2], [0, 3]], [[0, 4], [0, 5], [0, 6]], [[0, 7], [0, 8], [0, 9]]]) - 0.1)[None].astype(np.float32)
+    valid = np.array([[True, True, True], [True, True, True], [True, True, False]])[None]
+    preds = [torch.zeros(1, 3, 3, 2) for _ in range(6)]
+    m = EndPointError()
+    for _ in range(3):
+        m.update_state([torch.from_numpy(flow_gt), torch.from_numpy(valid)], preds)
+    info = m.result()
+    # valid pixels have gt (−0.1, k − 0.1), k = 1..8: epe = sqrt(0.01 + (k − 0.1)^2)
+    k = np.arange(1, 9) - 0.1
+    epe = np.sqrt(0.01 + k ** 2)
+    np.testing.assert_almost_equal(info['epe'], epe.mean(), decimal=5)
+    np.testing.assert_almost_equal(info['u1'], (epe < 1).mean(), decimal=6)
+    np.testing.assert_almost_equal(info['u3'], (epe < 3).mean(), decimal=6)
+    np.testing.assert_almost_equal(info['u5'], (epe < 5).mean(), decimal=6)
+    assert m.count == 3

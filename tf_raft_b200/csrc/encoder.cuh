@@ -261,31 +261,11 @@ inline int enc_conv_tc(const EncCtx& c, const EncConvSlot& cs, const EncNormSlot
   return tc_launch(p, 1, c.st);
 }
 
-inline int encoder_forward_group(int variant, int norm_type, int out_dim, const void* prepared, const float* images, int N,
-                                 int H, int W, int training, int image_norm, float* out, void* ws, size_t ws_bytes, cudaStream_t st);
-
-// Images are independent unless BatchNorm runs on batch statistics, so a large batch is processed in groups of a few images:
-// a group's raw convolution output (fp32), its statistics pass and its normalise / re-split pass then stay inside the
-// 126 MB L2 instead of streaming 117 MB tensors (8 images, 224 x 256 x 64) through HBM three times per layer.
-// RAFT_B200_ENC_IMAGES=<n> sets the group size (0 = whole batch).
+// (Processing a large batch in groups of 2 or 4 images, so that a group's raw convolution output stays in L2 between the
+// convolution, the statistics pass and the normalise pass, was measured in round 2: 408 / 456 vs 482 pairs/s -- the
+// smaller launches cost more than the L2 hits save -- and removed.)
 inline int encoder_forward(int variant, int norm_type, int out_dim, const void* prepared, const float* images, int N,
                            int H, int W, int training, int image_norm, float* out, void* ws, size_t ws_bytes, cudaStream_t st) {
-  static const int group = [] { const char* e = getenv("RAFT_B200_ENC_IMAGES"); return e ? atoi(e) : 0; }();
-  const bool batch_stats = norm_type == NORM_BATCH && training;
-  if (group <= 0 || group >= N || batch_stats)
-    return encoder_forward_group(variant, norm_type, out_dim, prepared, images, N, H, W, training, image_norm, out, ws, ws_bytes, st);
-  if (enc_ws_layout(nullptr, variant, N, H, W).total > ws_bytes) return RAFT_ERR_WORKSPACE;
-  const size_t in_img = (size_t)H * W * 3, out_img = (size_t)((H + 7) / 8) * ((W + 7) / 8) * out_dim;
-  for (int n0 = 0; n0 < N; n0 += group) {
-    const int n = std::min(group, N - n0);
-    RAFT_TRY(encoder_forward_group(variant, norm_type, out_dim, prepared, images + n0 * in_img, n, H, W, training, image_norm,
-                                   out + n0 * out_img, ws, ws_bytes, st));
-  }
-  return raft_launch_status();
-}
-
-inline int encoder_forward_group(int variant, int norm_type, int out_dim, const void* prepared, const float* images, int N,
-                                 int H, int W, int training, int image_norm, float* out, void* ws, size_t ws_bytes, cudaStream_t st) {
   EncCtx c;
   c.prep = reinterpret_cast<const uint8_t*>(prepared);
   c.L = enc_layout(variant, out_dim);

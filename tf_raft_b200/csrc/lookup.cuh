@@ -20,10 +20,19 @@ namespace raft {
 constexpr int kWinPitch = 20;     // floats per window row: 16 columns + 4 (banks of the three row groups stay apart)
 constexpr int kWinRows = 11;
 
+// Per-item state that travels from the set-up / load phase to the tap phase one loop iteration later.
+struct LookupItem {
+  float w1, w0;          // this lane's axis set-up (lanes [0,S): x, [S,2S): y): weights of the floor / ceil corner
+  int off0, off1;        // ... and window offsets of the two corners (x: columns, y: rows * pitch)
+  int ok;                // footprint fits the window (always, by construction; else the item takes the gather escape)
+  float cx, cy;          // level coordinates (escape path only)
+};
+
 template <int R, int L, bool kVec, bool kHalf>
-__global__ void __launch_bounds__(256, 5) corr_lookup_win_kernel(const LookupParams p) {
+__global__ void __launch_bounds__(256, 4) corr_lookup_win_kernel(const LookupParams p) {
   constexpr int S = 2 * R + 1, NT = S * S;
   constexpr int NJ = (S + 2) / 3;                                   // taps per lane
+  constexpr int NV = kVec ? 2 : 6;                                  // window registers per lane (float4 / float)
   static_assert(S <= 10 && 3 * S <= 32, "lane = (a, b mod 3) needs 3 * (2r+1) lanes");
   static_assert((L & (L - 1)) == 0, "level = work item mod L must be constant per warp (grid stride is a multiple of L)");
   __shared__ float4 ax_s[8][32];                                    // per warp: [0,16) x set-ups, [16,32) y set-ups
@@ -51,45 +60,75 @@ __global__ void __launch_bounds__(256, 5) corr_lookup_win_kernel(const LookupPar
   const int i = min(isy ? lane - S : lane, S - 1);
   const float fi = (float)(i - R), fmax_dim = (float)((isy ? H : W) - 1);
   const int t0 = a * S + bq;                                        // x-major tap order (corr.py:133-143): t = a * S + b
-  float2 cnext = make_float2(0.f, 0.f);
-  if (q0 < (unsigned)p.nq) cnext = __ldg(cptr);
-  for (unsigned q = q0; q < (unsigned)p.nq; q += qstep) {
-    const float2 c = cnext;
-    if (q + qstep < (unsigned)p.nq) cnext = __ldg(cptr + qstep);    // next item's coordinates
-    cptr += qstep;
+  // window element k of this lane sits at (row, column) = (wrow(k), wcol(k)) of the footprint
+  auto wrow = [&](int k) { const int e = lane + 32 * k; return kVec ? e >> 2 : e >> 4; };
+  auto wcol = [&](int k) { const int e = lane + 32 * k; return kVec ? (e & 3) << 2 : e & 15; };
+
+  // Software pipeline: the set-up and the footprint LOADS of item n+1 are issued before the taps of item n are
+  // evaluated, so every warp has one footprint in flight while it computes (the kernel is latency-bound otherwise:
+  // ~10 items per warp, each a DRAM round trip).
+  LookupItem it;
+  float4 wv4[kVec ? NV : 1];
+  float wv1[kVec ? 1 : NV];
+  unsigned wmask = 0;                                               // which of this lane's window elements are loaded
+
+  auto stage = [&](float2 c, const float* img_q) {                  // set-up + loads of one item
     const float cx = __fmul_rn(c.x, inv), cy = __fmul_rn(c.y, inv); // coords / 2**i  (corr.py:141)
-    // ---- 1. axis set-ups ----
     const float g = fminf(fmaxf(__fadd_rn(isy ? cy : cx, fi), 0.0f), fmax_dim);   // centroid + delta, clamp
     const float g0 = floorf(g), g1 = ceilf(g);
     const int i0 = (int)g0, i1 = (int)g1;
     const int bx = __shfl_sync(0xffffffffu, i0, 0), by = __shfl_sync(0xffffffffu, i0, S);
     const int ex = __shfl_sync(0xffffffffu, i1, S - 1), ey = __shfl_sync(0xffffffffu, i1, 2 * S - 1);
     const int bxa = kVec ? (bx & ~3) : bx;                          // first window column (16-byte aligned when vectorised)
-
-    if (ex - bxa < 16 && ey - by < kWinRows) {                      // always, by construction of the set-ups (<= 10 apart)
-      __syncwarp();                                                 // previous item's readers are done with ax / win
-      if (lane < 2 * S)
-        ax[(isy ? 16 : 0) + i] = make_float4(__fsub_rn(g1, g), __fsub_rn(g, g0),
-                                             __int_as_float(isy ? (i0 - by) * kWinPitch : i0 - bxa),
-                                             __int_as_float(isy ? (i1 - by) * kWinPitch : i1 - bxa));
-      // ---- 2. footprint -> shared memory ----
-      const float* src = img + by * W + bxa;
-      if constexpr (kVec) {
+    it.w1 = __fsub_rn(g1, g);
+    it.w0 = __fsub_rn(g, g0);
+    it.off0 = isy ? (i0 - by) * kWinPitch : i0 - bxa;
+    it.off1 = isy ? (i1 - by) * kWinPitch : i1 - bxa;
+    it.ok = (ex - bxa < 16 && ey - by < kWinRows) ? 1 : 0;
+    it.cx = cx;
+    it.cy = cy;
+    wmask = 0;
+    if (it.ok) {
+      const float* src = img_q + by * W + bxa;
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          const int e = lane + 32 * k, r = e >> 2, c4 = (e & 3) << 2;
-          if (r < kWinRows && by + r <= ey && bxa + c4 <= ex)
-            *reinterpret_cast<float4*>(win + r * kWinPitch + c4) = __ldg(reinterpret_cast<const float4*>(src + r * W + c4));
-        }
-      } else {
-#pragma unroll
-        for (int k = 0; k < 6; ++k) {                               // 11 rows x 16 columns, one texel per lane and step
-          const int e = lane + 32 * k, r = e >> 4, cc = e & 15;
-          if (r < kWinRows && by + r <= ey && bxa + cc <= ex) win[r * kWinPitch + cc] = __ldg(src + r * W + cc);
+      for (int k = 0; k < NV; ++k) {
+        const int r = wrow(k), cc = wcol(k);
+        if (r < kWinRows && by + r <= ey && bxa + cc <= ex) {
+          wmask |= 1u << k;
+          if constexpr (kVec) wv4[k] = __ldg(reinterpret_cast<const float4*>(src + r * W + cc));
+          else wv1[k] = __ldg(src + r * W + cc);
         }
       }
-      __syncwarp();
-      // ---- 3. taps ----
+    }
+  };
+
+  if (q0 < (unsigned)p.nq) stage(__ldg(cptr), img);
+  float2 cnext = make_float2(0.f, 0.f);
+  if (q0 + qstep < (unsigned)p.nq) cnext = __ldg(cptr + qstep);
+  for (unsigned q = q0; q < (unsigned)p.nq; q += qstep) {
+    // ---- publish the staged item (set-ups, footprint) to shared memory ----
+    const int ok = it.ok;
+    const float ecx = it.cx, ecy = it.cy;
+    __syncwarp();                                                   // previous item's readers are done with ax / win
+    if (lane < 2 * S) ax[(isy ? 16 : 0) + i] = make_float4(it.w1, it.w0, __int_as_float(it.off0), __int_as_float(it.off1));
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      if ((wmask >> k) & 1u) {
+        if constexpr (kVec) *reinterpret_cast<float4*>(win + wrow(k) * kWinPitch + wcol(k)) = wv4[k];
+        else win[wrow(k) * kWinPitch + wcol(k)] = wv1[k];
+      }
+    }
+    __syncwarp();
+    // ---- stage the next item: its loads are in flight while this one's taps are evaluated ----
+    const float* img_cur = img;
+    if (q + qstep < (unsigned)p.nq) {
+      const float2 c = cnext;
+      cptr += qstep;
+      if (q + 2 * qstep < (unsigned)p.nq) cnext = __ldg(cptr + qstep);
+      stage(c, img + img_step);
+    }
+    // ---- taps of the current item ----
+    if (ok) {
       if (a < S) {
         const float4 sx = ax[a];                                    // (w1, w0, off0, off1)
         const float* w0p = win + __float_as_int(sx.z);
@@ -117,7 +156,7 @@ __global__ void __launch_bounds__(256, 5) corr_lookup_win_kernel(const LookupPar
     } else {                                                        // escape: gather per tap (never taken in practice)
       for (int t = lane; t < NT; t += 32) {
         const int ta = t / S, tb = t - ta * S;
-        const float v = sample_floor_ceil(img, H, W, __fadd_rn(cx, (float)(ta - R)), __fadd_rn(cy, (float)(tb - R)));
+        const float v = sample_floor_ceil(img_cur, H, W, __fadd_rn(ecx, (float)(ta - R)), __fadd_rn(ecy, (float)(tb - R)));
         if constexpr (kHalf) {
           __half hh, ll;
           split_f16(v, hh, ll);
@@ -150,7 +189,7 @@ inline bool lookup_win_launch(const LookupParams& p, int levels, int radius, cud
   bool vec = true;                                                  // 128-bit loads need 16-byte aligned rows on every level
   for (int l = 0; l < levels; ++l)
     vec = vec && (p.lw[l] % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.pyr[l]) & 15) == 0);
-  const int grid = grid_for(nwork * 32, 256, kNumSMs * 5);           // 5 resident blocks per SM (48 registers): one wave
+  const int grid = grid_for(nwork * 32, 256, kNumSMs * 4);           // 4 resident blocks per SM (64 registers): one wave
   const bool half = p.out_hi != nullptr;
   if (half == (p.out != nullptr)) return false;                      // exactly one of the two output forms
 #define RAFT_LOOKUP_LAUNCH(RR, VV, HH) corr_lookup_win_kernel<RR, 4, VV, HH><<<grid, 256, 0, st>>>(p)

@@ -32,3 +32,28 @@ def end_point_error(y_true, y_pred, max_flow=400):
     epe = torch.sqrt(torch.sum((pred - flow_gt) ** 2, dim=-1))[valid]
     return {'epe': epe.mean(), 'u1': (epe < 1).float().mean(), 'u3': (epe < 3).float().mean(),
             'u5': (epe < 5).float().mean()}
+
+
+class EndPointError:
+    """Reference losses.py:46-85: the streaming metric -- per update the means of epe / <1 / <3 / <5 px over the valid
+    pixels of the LAST prediction are accumulated; result() is their average over the updates."""
+
+    def __init__(self, max_flow=400, **kwargs):
+        self.max_flow = max_flow
+        self.reset_states()
+
+    def reset_states(self):
+        self.epe = self.u1 = self.u3 = self.u5 = 0.0
+        self.count = 0
+
+    def update_state(self, y_true, y_pred):
+        info = end_point_error(y_true, y_pred[-1], self.max_flow)
+        self.epe += float(info['epe'])
+        self.u1 += float(info['u1'])
+        self.u3 += float(info['u3'])
+        self.u5 += float(info['u5'])
+        self.count += 1
+
+    def result(self):
+        n = max(self.count, 1)
+        return {'epe': self.epe / n, 'u1': self.u1 / n, 'u3': self.u3 / n, 'u5': self.u5 / n}

@@ -59,9 +59,13 @@ def max_over_ranks(value, device, group=None):
     return float(t.item())
 
 
-def predict_stream(predict_fn, batches, device):
+def predict_stream(predict_fn, batches, device, reuse_host_buffers=False):
     """Pipelined inference over host batches: yields `predict_fn(image1, image2)` for every `(image1, image2)` pair of
     `batches` as host tensors, in order.
+
+    `reuse_host_buffers=True` reads the results back into a ring of three pinned buffers instead of allocating a pinned
+    tensor per step (cudaHostAlloc costs as much as a forward): a yielded tensor is then valid until two further results
+    have been consumed.
 
     On a CUDA device the upload of pair i+1 is issued on a copy stream while pair i computes on the current stream, and
     the result of pair i is read back asynchronously into pinned memory while pair i+1 computes; pass pinned host
@@ -82,6 +86,21 @@ def predict_stream(predict_fn, batches, device):
             ready.record(copy)
         return a, b, ready
 
+    ring, ring_pos = [], 0
+
+    def host_buffer(like):
+        nonlocal ring_pos
+        if not reuse_host_buffers:
+            return torch.empty(like.shape, dtype=like.dtype, pin_memory=True)
+        slot = ring_pos % 3
+        ring_pos += 1
+        if slot >= len(ring):
+            ring.append(None)                      # slots fill in order 0, 1, 2
+        buf = ring[slot]
+        if buf is None or buf.shape != like.shape or buf.dtype != like.dtype:
+            buf = ring[slot] = torch.empty(like.shape, dtype=like.dtype, pin_memory=torch.cuda.is_available())
+        return buf
+
     it = iter(batches)
     first = next(it, None)
     if first is None:
@@ -97,7 +116,7 @@ def predict_stream(predict_fn, batches, device):
             b.record_stream(main)
         out = predict_fn(a, b)
         if cuda:
-            host_out = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+            host_out = host_buffer(out)
             host_out.copy_(out, non_blocking=True)                    # stream-ordered after the compute, before the next one
             done = torch.cuda.Event()
             done.record(main)

@@ -174,13 +174,18 @@ def test_train_step_vs_oracle_autograd(variant, shape, iters):
         tol = 5e-2 * float(want.abs().max()) + 2e-6       # (biases in front of a norm layer have a zero true gradient: noise)
         assert float((got_g - want).abs().max()) <= tol, f'gradient of {k}: max error {float((got_g - want).abs().max()):.3e} (scale {float(want.abs().max()):.3e})'
     assert math.sqrt(num / den) <= 1e-2, f'relative L2 error of the whole gradient {math.sqrt(num / den):.3e}'
+    # updated values.  Adam's first step is lr * g / (|g| + eps'): a sign-like function of the gradient, so an entry whose
+    # gradient is tiny relative to the tensor's is decided by rounding; the comparison is made where the gradient is
+    # well-determined (|g| >= 1 % of the tensor's largest), on the UPDATE (new - old), to 5 % of the learning rate.
     got = {k: v.cpu() for k, v in model.state_dict().items()}
     worst = 0.0
     for k, want in new_o.items():
-        if float(grads_o[k].abs().max()) < 1e-5:            # zero true gradient: Adam turns rounding noise into the step
+        g = grads_o[k]
+        sel = g.abs() >= 1e-2 * g.abs().max()
+        if float(g.abs().max()) < 1e-5 or not bool(sel.any()):          # zero true gradient: noise
             continue
-        denom = float(want.abs().max()) + 1e-12
-        err = float((got[k] - want).abs().max()) / denom
+        old = torch.from_numpy(np.asarray(p[k], dtype=np.float32))
+        err = float(((got[k] - old) - (want - old))[sel].abs().max()) / lr
         worst = max(worst, err)
-        assert err <= 2e-4, f'{k}: relative max error {err:.2e} after one step (global norm oracle {norm_o:.4f})'
-    print(f'{variant}: loss {out["loss"]:.6f} (oracle {loss_o:.6f}), worst relative parameter error {worst:.2e}')
+        assert err <= 5e-2, f'{k}: update differs by {err:.3f} x lr (global norm oracle {norm_o:.4f})'
+    print(f'{variant}: loss {out["loss"]:.6f} (oracle {loss_o:.6f}), worst update error {worst:.3f} x lr')

@@ -215,6 +215,11 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// Same, for an operand whose first row is `row_shift` (0..7) rows of 128 B past a 1024-byte boundary: the matrix base
+// offset field [49,52) = (start address >> 7) & 7 tells the swizzle which row phase the first row has.
+__device__ __forceinline__ uint64_t make_desc_sw128_shifted(uint32_t smem_addr, uint32_t base_offset) {
+  return make_desc_sw128(smem_addr) | ((uint64_t)(base_offset & 7u) << 49);
+}
 // kind::f16 instruction descriptor: D=f32 (bits 4-5 = 1), A=B=f16 (0), both K-major, N>>3 at
 // [17,23), M>>4 at [24,29).
 __device__ __forceinline__ uint32_t make_idesc_f16(int m, int n) {

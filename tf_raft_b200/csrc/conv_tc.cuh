@@ -41,6 +41,8 @@ constexpr int kChunkK = 64;                       // fp16 elements per 128-byte 
 constexpr int kABytes = kTileM * kChunkK * 2;     // 16 KiB per A plane per stage
 constexpr int kEpiPatchBytes = 16 * 2048;         // EPI_GRU_Q: transposition patches of the 16 epilogue warps
 constexpr int kSmemBudget = 227 * 1024 - 2048;
+constexpr int kARow3Pixels = 136;                 // kRow3: activation box width (1 + 128 + 1 pixels, padded to a multiple of 8)
+constexpr int kARow3Bytes = 2 * kARow3Pixels * kChunkK * 2;   // hi + lo planes of one 136-pixel row chunk: 34 KB
 
 struct alignas(64) TcConvParams {
   CUtensorMap a_map[2];           // (hi, lo) plane pair of up to two channel-concatenated sources (K segments)
@@ -70,6 +72,13 @@ struct alignas(64) TcConvParams {
   // attribute, so this grid's CTAs may be scheduled -- and run their prologue -- while the previous kernel in the stream
   // drains; every thread then executes griddepcontrol.wait before touching global memory.
   int pdl;
+  // kRow3 instantiation (3x3, stride 1, 1 x 128 pixel tiles, cout <= 96: the wide encoder layers).  The three taps of a
+  // kernel row read the SAME image row shifted by one pixel, so a stage holds ONE activation box of 136 pixels (x0-1 ..
+  // x0+134; 136 * 128 B = 17 KB per plane keeps the lo plane on a 1024-byte boundary) and ONE weight box with the row's
+  // three taps; tap dx issues its MMAs on the activation rows [dx, dx + 128) through a descriptor whose start is shifted by
+  // dx * 128 bytes.  3 + 3 boxes per 64-channel chunk instead of 9 + 9: these layers are bound by TMA box delivery.
+  int row3;
+  int row3_base_mode;      // 1: shifted descriptors carry base_offset = dx (PTX matrix-descriptor rule); 0: base_offset 0
   // EPI_LINEAR with n_total == 2 (flow_head.conv2) inside the iteration loop: coords1 += delta_flow and
   // flow = coords1 - coords0 (model.py:102, :97) are applied by the thread that holds the pixel's two output columns.
   float* adv_coords;                       // (px, 2) coords1, updated in place; null = no fused advance
@@ -305,7 +314,7 @@ __device__ __forceinline__ void tc_epilogue_q_t(const TcConvParams& p, float (&v
 
 // kRowEpi selects the epilogue form at compile time: thread-per-row registers (EPI_LINEAR, EPI_GRU_ZR) or transposed through
 // shared-memory patches (EPI_GRU_Q), so that neither costs the other registers or code.
-template <bool kRowEpi>
+template <bool kRowEpi, bool kRow3 = false>
 __global__ void __launch_bounds__(64 + 32 * kEpiWarpsConv, 1) conv_tc_kernel(const __grid_constant__ TcConvParams p) {
 #if defined(__CUDA_ARCH__)
   // Persistent: CTA c processes output tiles c, c + gridDim.x, ...  A tile is (pixel tile, column tile).  All
@@ -331,7 +340,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarpsConv, 1) conv_tc_kernel(con
   const int ntiles = mtiles * p.n_tiles_n;
   const int ntaps = p.kh * p.kw;
   const int chunks_per_tap = p.seg_chunks[0] + (p.nseg > 1 ? p.seg_chunks[1] : 0);
-  const int total = ntaps * chunks_per_tap;               // K chunks per tile
+  const int total = (kRow3 ? p.kh : ntaps) * chunks_per_tap;   // stages per tile (kRow3: one per kernel row and chunk)
   const int gsz = p.group_chunks;
   const int ngroups = (total + gsz - 1) / gsz;            // promotion groups per tile
   const int nchunks32 = (p.bn + 31) >> 5;                 // 32-column accumulator chunks
@@ -377,7 +386,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarpsConv, 1) conv_tc_kernel(con
       if (p.pdl) {
         // Convolution weights do not depend on the previous grid: fetch them for the first stages of this CTA's first
         // tile while that grid is still draining, then wait, then fetch the activations.
-        if ((int)blockIdx.x < ntiles) {
+        if (!kRow3 && (int)blockIdx.x < ntiles) {
           const int n0 = ((int)blockIdx.x / mtiles) * p.bn;
           npre = min(nst, total);
 #pragma unroll 1
@@ -398,6 +407,20 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarpsConv, 1) conv_tc_kernel(con
         const int ty = mt % p.tiles_y;
         const int b = mt / p.tiles_y;
         const int x0 = tx * p.TW * p.stride, y0 = ty * p.TH * p.stride, n0 = nt * p.bn;
+        if constexpr (kRow3) {
+          for (int ky = 0; ky < p.kh; ++ky) {
+            for (int ch = 0; ch < p.seg_chunks[0]; ++ch, ++it) {
+              const int s = it % nst;
+              mbar_wait(&empty_bar[s], ((uint32_t)(it / nst) & 1u) ^ 1u);
+              if (p.dbg && blockIdx.x == 0 && it < 512) p.dbg[it] = clock64();              // slot free
+              uint8_t* st = stages + (size_t)s * p.stage_bytes;
+              mbar_arrive_expect_tx(&full_bar[s], (uint32_t)p.stage_bytes);
+              tma_load_5d(st, &p.a_map[0], &full_bar[s], p.seg_c0[0] + ch * kChunkK, x0 - p.pw, y0 + ky - p.ph, b, 0);
+              tma_load_4d(st + kARow3Bytes, &p.b_map, &full_bar[s], ch * kChunkK, n0, ky * p.kw, 0);
+            }
+          }
+          continue;
+        }
         for (int tap = 0; tap < ntaps; ++tap) {
           const int dy = tap / p.kw - p.ph, dx = tap % p.kw - p.pw;
           int kc = 0;
@@ -439,17 +462,36 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarpsConv, 1) conv_tc_kernel(con
           if (p.dbg && blockIdx.x == 0 && it < 512 && lane == 0) p.dbg[512 + it] = clock64();   // data landed
           if (elect_one()) {
             const uint32_t sa = smem_u32(stages + (size_t)s * p.stage_bytes);
-            const uint64_t a_hi = make_desc_sw128(sa);
-            const uint64_t a_lo = make_desc_sw128(sa + kABytes);
-            const uint64_t b_hi = make_desc_sw128(sa + 2 * kABytes);
-            const uint64_t b_lo = make_desc_sw128(sa + 2 * kABytes + b_bytes);
+            if constexpr (kRow3) {
+              // stage = [A hi: 136 rows | A lo: 136 rows | W hi: tap 0, 1, 2 | W lo: tap 0, 1, 2]
+#pragma unroll 1
+              for (int dx = 0; dx < 3; ++dx) {
+                const uint32_t bo = p.row3_base_mode ? (uint32_t)dx : 0u;
+                const uint64_t a_hi = make_desc_sw128_shifted(sa + dx * 128, bo);
+                const uint64_t a_lo = make_desc_sw128_shifted(sa + kARow3Bytes / 2 + dx * 128, bo);
+                const uint64_t b_hi = make_desc_sw128(sa + kARow3Bytes + dx * b_bytes);
+                const uint64_t b_lo = make_desc_sw128(sa + kARow3Bytes + (3 + dx) * b_bytes);
 #pragma unroll
-            for (int k = 0; k < kChunkK / 16; ++k)   // +32 bytes per K=16 step == +2 in 16-byte units
-              umma_f16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (!first || k > 0) ? 1u : 0u);
+                for (int k = 0; k < kChunkK / 16; ++k)
+                  umma_f16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (!first || dx > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
-            for (int k = 0; k < kChunkK / 16; ++k) umma_f16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+                for (int k = 0; k < kChunkK / 16; ++k) umma_f16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
 #pragma unroll
-            for (int k = 0; k < kChunkK / 16; ++k) umma_f16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+                for (int k = 0; k < kChunkK / 16; ++k) umma_f16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+              }
+            } else {
+              const uint64_t a_hi = make_desc_sw128(sa);
+              const uint64_t a_lo = make_desc_sw128(sa + kABytes);
+              const uint64_t b_hi = make_desc_sw128(sa + 2 * kABytes);
+              const uint64_t b_lo = make_desc_sw128(sa + 2 * kABytes + b_bytes);
+#pragma unroll
+              for (int k = 0; k < kChunkK / 16; ++k)   // +32 bytes per K=16 step == +2 in 16-byte units
+                umma_f16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (!first || k > 0) ? 1u : 0u);
+#pragma unroll
+              for (int k = 0; k < kChunkK / 16; ++k) umma_f16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+#pragma unroll
+              for (int k = 0; k < kChunkK / 16; ++k) umma_f16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+            }
             umma_commit(&empty_bar[s]);                      // frees the smem slot once these MMAs retire
             if (done == gend - 1) umma_commit(&acc_full[buf]);   // group complete -> promotion warps
           }
@@ -604,6 +646,7 @@ inline int tc_finalize(TcConvParams& p) {
   p.tiles_x = ceil_div(p.W, p.TW);
   p.tiles_y = ceil_div(p.H, p.TH);
   p.stage_bytes = 2 * kABytes + 2 * p.bn * kChunkK * 2;
+  if (p.row3) p.stage_bytes = kARow3Bytes + 3 * 2 * p.bn * kChunkK * 2;
   const int patch = tc_uses_patch(p.mode) ? kEpiPatchBytes : 0;   // 16 x 2 KB patches (GRU q)
   int nst = (kSmemBudget - patch) / p.stage_bytes;
   if (nst > 8) nst = 8;
@@ -635,6 +678,7 @@ inline int tc_launch(TcConvParams& p, int n_tiles_n, cudaStream_t stream) {
   if (!(attr_set_mask & dev_bit)) {
     RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    RAFT_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set_mask |= dev_bit;
   }
   const int mtiles = p.B * p.tiles_y * p.tiles_x;
@@ -643,7 +687,10 @@ inline int tc_launch(TcConvParams& p, int n_tiles_n, cudaStream_t stream) {
   const unsigned grid = (unsigned)(ntiles < kNumSMs ? ntiles : kNumSMs);   // one persistent CTA per SM
   p.pdl = tc_pdl_enabled() ? 1 : 0;
   const int threads = 64 + 32 * kEpiWarpsConv;
-  void (*kern)(TcConvParams) = p.mode == EPI_GRU_Q ? conv_tc_kernel<false> : conv_tc_kernel<true>;
+  if (p.row3 && (p.mode != EPI_LINEAR || p.kh != 3 || p.kw != 3 || p.stride != 1 || p.TH != 1 || p.TW != kTileM || p.nseg != 1 ||
+                 p.bn % 8 != 0 || n_tiles_n != 1))
+    return RAFT_ERR_UNSUPPORTED;
+  void (*kern)(TcConvParams) = p.mode == EPI_GRU_Q ? conv_tc_kernel<false> : (p.row3 ? conv_tc_kernel<true, true> : conv_tc_kernel<true>);
   if (!p.pdl) {
     kern<<<grid, threads, smem, stream>>>(p);
   } else {                                             // programmatic-serialization attribute: see the kernel prologue

@@ -6,12 +6,13 @@
 // plus one preparation kernel that pools fmap2 and splits both feature maps into the fp16 (hi, lo) operand planes.
 //
 // Tile = 128 queries x bn targets (bn <= 256), K = C in 64-channel chunks, three fp16 passes per chunk (hi*hi, lo*hi,
-// hi*lo; fp32-grade), one accumulation chain of 12 * C / 64 MMAs per tile in TMEM (48 at C = 256:
-// the tensor core's truncating fp32 accumulation costs ~2e-6 relative there, inside the 2e-5 pyramid tolerance, so no
-// register promotion is needed and the two TMEM buffers double-buffer whole tiles).
-// Warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..9 = store: each store warp owns 32 queries
-// (its TMEM lane quarter) x 128 columns, transposes 32 x 32 blocks through a swizzled 4 KB shared-memory patch and
-// writes full 128-byte lines of the pyramid rows.  The tile list runs over all levels (level 0 first), consecutive CTAs
+// hi*lo; fp32-grade), accumulation in TMEM with an IEEE-fp32 promotion into registers every two
+// chunks (24-MMA chains, exactly the arithmetic of every other tensor-core layer; a single 48-MMA chain per tile was tried
+// -- it is inside the pyramid tolerance, but its ~1e-6 relative difference moved one query of the benchmark pair across a
+// discontinuity of the reference sampler at iteration 4).
+// Warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..17 = promotion + store: each store warp owns 32 queries
+// (its TMEM lane quarter) x 64 columns, transposes 32 x 16 blocks through a swizzled 2 KB shared-memory patch and
+// writes 64-byte row segments (8 rows per store instruction).  The tile list runs over all levels (level 0 first), consecutive CTAs
 // take consecutive query tiles of the same target tile, so the target features are shared through L2.
 // Everything in the store path is inlined and register-resident: the round-1 form of this epilogue lived in a
 // non-inlined routine whose call made ptxas spill accumulators to local memory (which, with 227 KB of the L1/shared
@@ -22,11 +23,11 @@
 
 namespace raft {
 
-constexpr int kCorrStoreWarps = 8;
+constexpr int kCorrStoreWarps = 16;
 constexpr int kCorrThreads = 64 + 32 * kCorrStoreWarps;
 constexpr int kCorrStageBytes = 2 * kABytes + 2 * 256 * kChunkK * 2;     // 96 KB: A (hi|lo) 32 KB + B (hi|lo) up to 64 KB
 constexpr int kCorrStages = 2;
-constexpr int kCorrPatchBytes = kCorrStoreWarps * 4096;
+constexpr int kCorrPatchBytes = kCorrStoreWarps * 2048;
 constexpr int kCorrSmemBytes = 1024 /*align slack*/ + kCorrStages * kCorrStageBytes + kCorrPatchBytes + 256 /*barriers*/;
 static_assert(kCorrSmemBytes <= 227 * 1024, "correlation kernel shared memory");
 
@@ -112,116 +113,135 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_tc_kernel(const __grid_c
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    int it = 0, tt = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tt) {
+    int it = 0, gg = 0;
+    const int ngroups = (chunks + 1) >> 1;             // promotion groups of two K chunks
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
       int l, nt, mt;
       decode(t, l, nt, mt);
       const int bn = p.bn[l];
       const uint32_t idesc = make_idesc_f16(kTileM, bn);
       const uint32_t b_lo_off = (uint32_t)(bn * kChunkK * 2);
-      const int buf = tt & 1;
-      mbar_wait(&acc_empty[buf], ((uint32_t)(tt >> 1) & 1u) ^ 1u);       // store warps have read this buffer out
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 256);
-      for (int kc = 0; kc < chunks; ++kc, ++it) {
-        const int s = it % kCorrStages;
-        mbar_wait(&full_bar[s], (uint32_t)(it / kCorrStages) & 1u);
+      int done = 0;
+      for (int g = 0; g < ngroups; ++g, ++gg) {
+        const int buf = gg & 1;
+        mbar_wait(&acc_empty[buf], ((uint32_t)(gg >> 1) & 1u) ^ 1u);       // promotion warps drained this buffer
         tc_fence_after();
-        if (p.dbg && blockIdx.x == 0 && it < 512 && lane == 0) p.dbg[512 + it] = clock64();
-        if (elect_one()) {
-          const uint32_t sa = smem_u32(stages + (size_t)s * kCorrStageBytes);
-          const uint64_t a_hi = make_desc_sw128(sa), a_lo = make_desc_sw128(sa + kABytes);
-          const uint64_t b_hi = make_desc_sw128(sa + 2 * kABytes), b_lo = make_desc_sw128(sa + 2 * kABytes + b_lo_off);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 256);
+        const int gend = min(chunks, done + 2);
+        for (int first = 1; done < gend; ++done, ++it, first = 0) {
+          const int s = it % kCorrStages;
+          mbar_wait(&full_bar[s], (uint32_t)(it / kCorrStages) & 1u);
+          tc_fence_after();
+          if (p.dbg && blockIdx.x == 0 && it < 512 && lane == 0) p.dbg[512 + it] = clock64();
+          if (elect_one()) {
+            const uint32_t sa = smem_u32(stages + (size_t)s * kCorrStageBytes);
+            const uint64_t a_hi = make_desc_sw128(sa), a_lo = make_desc_sw128(sa + kABytes);
+            const uint64_t b_hi = make_desc_sw128(sa + 2 * kABytes), b_lo = make_desc_sw128(sa + 2 * kABytes + b_lo_off);
 #pragma unroll
-          for (int k = 0; k < kChunkK / 16; ++k) umma_f16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (kc > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < kChunkK / 16; ++k) umma_f16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (!first || k > 0) ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < kChunkK / 16; ++k) umma_f16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+            for (int k = 0; k < kChunkK / 16; ++k) umma_f16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
 #pragma unroll
-          for (int k = 0; k < kChunkK / 16; ++k) umma_f16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
-          umma_commit(&empty_bar[s]);
-          if (kc == chunks - 1) umma_commit(&acc_full[buf]);
+            for (int k = 0; k < kChunkK / 16; ++k) umma_f16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+            umma_commit(&empty_bar[s]);
+            if (done == gend - 1) umma_commit(&acc_full[buf]);
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
   } else {
-    // ===================== store (warps 2..9) =====================
+    // ===================== promotion + store (warps 2..17) =====================
     const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
-    const int part = (warp - 2) >> 2;                // columns [part * 128, part * 128 + 128) of the tile
-    const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(part * 128);
-    float* patch = patches + (warp - 2) * 1024;
-    const int rsub = lane >> 3, q4 = lane & 7;
-    int tt = 0;
+    const int part = (warp - 2) >> 2;                // columns [part * 64, part * 64 + 64) of the tile
+    const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(part * 64);
+    float4* patch4 = reinterpret_cast<float4*>(patches + (warp - 2) * 512);
+    const int c4 = lane & 3, r8 = lane >> 2;
+    const int wsw = (lane >> 1) & 3, rsw = (lane >> 3) & 3;   // XOR swizzles: conflict-free 16-byte writes and reads
+    const int ngroups = (chunks + 1) >> 1;
+    int gg = 0, tt = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tt) {
       int l, nt, mt;
       decode(t, l, nt, mt);
       const int bn = p.bn[l], n2 = p.n2[l];
-      const int b = mt / p.mtiles_img, m0 = (mt - b * p.mtiles_img) * kTileM, n0 = nt * bn;
       // 32-column blocks of this warp in this tile that hold columns of the level (warp-uniform)
-      const int nblk = max(0, min(4, (min(bn, n2 - n0) - part * 128 + 31) >> 5));
-      const int buf = tt & 1;
-      const int row_base = m0 + quarter * 32;                              // first query of this warp's 32 rows
-      float* dst0 = p.out[l] + ((size_t)b * p.N + row_base + rsub) * n2 + n0 + part * 128 + 4 * q4;
-      const bool vec = (n2 & 3) == 0;
-      mbar_wait(&acc_full[buf], (uint32_t)(tt >> 1) & 1u);
-      tc_fence_after();
-      if (p.dbg && blockIdx.x == 0 && tt < 256 && warp == 2 && lane == 0) p.dbg[1024 + tt] = clock64();
+      const int nblk = max(0, min(2, (min(bn, n2 - nt * bn) - part * 64 + 31) >> 5));
+
+      float racc[2][32];
+#pragma unroll
+      for (int ci = 0; ci < 2; ++ci)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) racc[ci][j] = 0.0f;
+
 #pragma unroll 1
-      for (int ci = 0; ci < nblk; ++ci) {
-        uint32_t r[32];
-        tmem_ld_32x32(trow + (uint32_t)(buf * 256 + ci * 32), r);
-        tmem_ld_wait();
-        if (ci == nblk - 1) {                                              // last read of this buffer: hand it back
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[buf]);
-          if (p.dbg && blockIdx.x == 0 && tt < 256 && warp == 2 && lane == 0) p.dbg[1536 + tt] = clock64();
-        }
-        __syncwarp();                                                      // previous block's readers are done with the patch
+      for (int g = 0; g < ngroups; ++g, ++gg) {
+        const int buf = gg & 1;
+        mbar_wait(&acc_full[buf], (uint32_t)(gg >> 1) & 1u);
+        tc_fence_after();
+        if (p.dbg && blockIdx.x == 0 && g == ngroups - 1 && tt < 256 && warp == 2 && lane == 0) p.dbg[1024 + tt] = clock64();
 #pragma unroll
-        for (int qq = 0; qq < 8; ++qq) {
-          float4 a4 = make_float4(__uint_as_float(r[4 * qq]), __uint_as_float(r[4 * qq + 1]), __uint_as_float(r[4 * qq + 2]),
-                                  __uint_as_float(r[4 * qq + 3]));
-          if (p.corr_mul != 0.0f) {
-            a4.x *= p.corr_mul; a4.y *= p.corr_mul; a4.z *= p.corr_mul; a4.w *= p.corr_mul;
-          } else {
-            a4.x = __fdiv_rn(a4.x, p.corr_div); a4.y = __fdiv_rn(a4.y, p.corr_div);
-            a4.z = __fdiv_rn(a4.z, p.corr_div); a4.w = __fdiv_rn(a4.w, p.corr_div);
+        for (int ci = 0; ci < 2; ++ci) {
+          if (ci < nblk) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              uint32_t r[16];
+              tmem_ld_32x16(trow + (uint32_t)(buf * 256 + ci * 32 + hh * 16), r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) racc[ci][hh * 16 + j] += __uint_as_float(r[j]);   // IEEE fp32 promotion
+            }
           }
-          *reinterpret_cast<float4*>(patch + lane * 32 + ((qq ^ (lane & 7)) << 2)) = a4;
         }
+        tc_fence_before();
         __syncwarp();
-        const int col = n0 + part * 128 + ci * 32 + 4 * q4;
-        float* dst = dst0 + ci * 32;
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        if (p.dbg && blockIdx.x == 0 && g == ngroups - 1 && tt < 256 && warp == 2 && lane == 0) p.dbg[1536 + tt] = clock64();
+      }
+
+      // ---- store: the issuer is already accumulating the next tile ----
+      const int b = mt / p.mtiles_img, m0 = (mt - b * p.mtiles_img) * kTileM, n0 = nt * bn;
+      const int row_base = m0 + quarter * 32;                              // first query of this warp's 32 rows
+      const bool vec = (n2 & 3) == 0;
+      float* dst0 = p.out[l] + ((size_t)b * p.N + row_base + r8) * n2 + n0 + part * 64 + 4 * c4;
 #pragma unroll
-        for (int i0 = 0; i0 < 8; i0 += 4) {                                // four 16-byte loads in flight, then four stores
-          float4 v[4];
+      for (int ci = 0; ci < 2; ++ci) {
+        if (ci < nblk) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int rr = 4 * (i0 + i) + rsub;
-            v[i] = *reinterpret_cast<const float4*>(patch + rr * 32 + ((q4 ^ (rr & 7)) << 2));
-          }
+          for (int hh = 0; hh < 2; ++hh) {
+            const int col = n0 + part * 64 + ci * 32 + hh * 16 + 4 * c4;
+            __syncwarp();                                                  // previous block's readers are done with the patch
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int row = row_base + 4 * (i0 + i) + rsub;
-            if (row < p.N && col < n2) {
-              float* d = dst + (size_t)(4 * (i0 + i)) * n2;
-              if (vec) {
-                *reinterpret_cast<float4*>(d) = v[i];
+            for (int q = 0; q < 4; ++q) {
+              float4 a4 = make_float4(racc[ci][hh * 16 + 4 * q], racc[ci][hh * 16 + 4 * q + 1], racc[ci][hh * 16 + 4 * q + 2],
+                                      racc[ci][hh * 16 + 4 * q + 3]);
+              if (p.corr_mul != 0.0f) {
+                a4.x *= p.corr_mul; a4.y *= p.corr_mul; a4.z *= p.corr_mul; a4.w *= p.corr_mul;
               } else {
-                d[0] = v[i].x;
-                if (col + 1 < n2) d[1] = v[i].y;
-                if (col + 2 < n2) d[2] = v[i].z;
-                if (col + 3 < n2) d[3] = v[i].w;
+                a4.x = __fdiv_rn(a4.x, p.corr_div); a4.y = __fdiv_rn(a4.y, p.corr_div);
+                a4.z = __fdiv_rn(a4.z, p.corr_div); a4.w = __fdiv_rn(a4.w, p.corr_div);
+              }
+              patch4[lane * 4 + (q ^ wsw)] = a4;                           // lane = row: 16 columns = 4 x 16 bytes
+            }
+            __syncwarp();
+            float* dst = dst0 + ci * 32 + hh * 16;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {                                  // rows r8 + 8k, columns 4 c4 .. 4 c4 + 3
+              const float4 v = patch4[(r8 + 8 * k) * 4 + (c4 ^ rsw)];
+              const int row = row_base + r8 + 8 * k;
+              if (row < p.N && col < n2) {
+                float* d = dst + (size_t)(8 * k) * n2;
+                if (vec) {
+                  *reinterpret_cast<float4*>(d) = v;
+                } else {
+                  d[0] = v.x;
+                  if (col + 1 < n2) d[1] = v.y;
+                  if (col + 2 < n2) d[2] = v.z;
+                  if (col + 3 < n2) d[3] = v.w;
+                }
               }
             }
           }
         }
-      }
-      if (nblk == 0) {                                                     // nothing to read: hand the buffer back at once
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[buf]);
       }
       if (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0 && tt < 255) p.dbg[1536 + 256 + tt] = clock64();
     }

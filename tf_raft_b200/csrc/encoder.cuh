@@ -218,10 +218,24 @@ inline int enc_conv_tc(const EncCtx& c, const EncConvSlot& cs, const EncNormSlot
   int tw, th;
   tc_pick_tile(Wout, Hout, &tw, &th);
   if (tw * stride > 256) tw = 128 / stride, th = 128 / tw;
-  RAFT_TRY(make_tmap_act2(&p.a_map[0], ahi, alo, c.N, Hin, Win, cs.cin_pad, tw, th, stride));
-  RAFT_TRY(make_tmap_wgt2(&p.b_map, reinterpret_cast<const __half*>(c.prep + cs.hi),
-                          reinterpret_cast<const __half*>(c.prep + cs.lo), cs.kh * cs.kw, cs.cout_pad, cs.cin_pad,
-                          cs.cout_pad));
+  // Wide 3x3 stride-1 layers with few output channels (layer1 / layer2 of both encoders at >= 128 feature columns): one
+  // activation box and one weight box per kernel ROW (conv_tc.cuh kRow3).  RAFT_B200_ROW3=0 disables, =2 uses descriptors
+  // without the base-offset field (A/B of the descriptor rule).
+  static const int row3_flag = [] { const char* e = getenv("RAFT_B200_ROW3"); return e ? atoi(e) : 1; }();
+  const bool row3 = row3_flag && cs.kh == 3 && cs.kw == 3 && stride == 1 && tw == kTileM && th == 1 && cs.cout_pad <= 96 &&
+                    cs.cout_pad % 8 == 0;
+  if (row3) {
+    RAFT_TRY(make_tmap_act2(&p.a_map[0], ahi, alo, c.N, Hin, Win, cs.cin_pad, kARow3Pixels, 1, 1));
+    RAFT_TRY(make_tmap_wgt3(&p.b_map, reinterpret_cast<const __half*>(c.prep + cs.hi),
+                            reinterpret_cast<const __half*>(c.prep + cs.lo), cs.kh * cs.kw, cs.cout_pad, cs.cin_pad, cs.cout_pad));
+    p.row3 = 1;
+    p.row3_base_mode = row3_flag == 2 ? 0 : 1;
+  } else {
+    RAFT_TRY(make_tmap_act2(&p.a_map[0], ahi, alo, c.N, Hin, Win, cs.cin_pad, tw, th, stride));
+    RAFT_TRY(make_tmap_wgt2(&p.b_map, reinterpret_cast<const __half*>(c.prep + cs.hi),
+                            reinterpret_cast<const __half*>(c.prep + cs.lo), cs.kh * cs.kw, cs.cout_pad, cs.cin_pad,
+                            cs.cout_pad));
+  }
   p.nseg = 1; p.seg_chunks[0] = cs.cin_pad / kChunkK; p.seg_c0[0] = 0;
   p.kh = cs.kh; p.kw = cs.kw; p.stride = stride;
   // Keras 'same': stride 1 -> (k-1)/2 before; stride 2 on even input -> total k-2, before = (k-2)/2 (0 for 3x3);
@@ -256,6 +270,7 @@ inline int enc_conv_tc(const EncCtx& c, const EncConvSlot& cs, const EncNormSlot
     // (its K = 1920 GRU contractions feed a 12-iteration recurrence).  Measured: 433 -> 447 pairs/s, parity tests green.
     static const int grp = [] { const char* e = getenv("RAFT_B200_ENC_GROUP"); return e ? atoi(e) : 5; }();
     if (grp > 0) p.group_chunks = grp;
+    if (row3) p.group_chunks = 2;       // a kRow3 stage carries three taps: 2 stages = 72 MMA steps per accumulation chain
   }
   ++g_launches;
   return tc_launch(p, 1, c.st);

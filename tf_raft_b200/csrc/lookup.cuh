@@ -47,13 +47,14 @@ __global__ void __launch_bounds__(256, 4) corr_lookup_win_kernel(const LookupPar
   const int H = p.lh[l], W = p.lw[l];
   const float inv = 1.0f / (float)(1 << l);                         // exact power of two
   const unsigned q0 = (blockIdx.x * 8u + wib) / L, qstep = gridDim.x * (8u / L);
-  const float* img = p.pyr[l] + (size_t)q0 * H * W;
-  const size_t img_step = (size_t)qstep * H * W;
+  // element offsets stay below 2^31 (host-checked), so the per-query advance is one 32-bit add per pointer
+  const float* const img_base = p.pyr[l];
+  unsigned img_off = q0 * (unsigned)(H * W);
+  const unsigned img_step = qstep * (unsigned)(H * W);
   const float2* cptr = reinterpret_cast<const float2*>(p.coords) + q0;
-  float* o = kHalf ? nullptr : p.out + (size_t)q0 * p.out_stride + l * NT;
-  __half* oh = kHalf ? p.out_hi + (size_t)q0 * p.h_stride + l * NT : nullptr;
-  __half* ol = kHalf ? p.out_lo + (size_t)q0 * p.h_stride + l * NT : nullptr;
-  const size_t o_step = (size_t)qstep * (kHalf ? p.h_stride : p.out_stride);
+  const unsigned ostride = (unsigned)(kHalf ? p.h_stride : p.out_stride);
+  unsigned o_off = q0 * ostride + (unsigned)(l * NT);
+  const unsigned o_step = qstep * ostride;
   const int npad = (kHalf && l == L - 1) ? p.h_pad - L * NT : 0;   // zero channels behind the last level (operand planes)
   // set-up lanes: [0,S) x, [S,2S) y (the other lanes compute a harmless duplicate)
   const bool isy = lane >= S;
@@ -82,8 +83,8 @@ __global__ void __launch_bounds__(256, 4) corr_lookup_win_kernel(const LookupPar
     const int bxa = kVec ? (bx & ~3) : bx;                          // first window column (16-byte aligned when vectorised)
     it.w1 = __fsub_rn(g1, g);
     it.w0 = __fsub_rn(g, g0);
-    it.off0 = isy ? (i0 - by) * kWinPitch : i0 - bxa;
-    it.off1 = isy ? (i1 - by) * kWinPitch : i1 - bxa;
+    it.off0 = (isy ? (i0 - by) * kWinPitch : i0 - bxa) * 4;           // BYTE offsets inside the window
+    it.off1 = (isy ? (i1 - by) * kWinPitch : i1 - bxa) * 4;
     it.ok = (ex - bxa < 16 && ey - by < kWinRows) ? 1 : 0;
     it.cx = cx;
     it.cy = cy;
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(256, 4) corr_lookup_win_kernel(const LookupPar
     }
   };
 
-  if (q0 < (unsigned)p.nq) stage(__ldg(cptr), img);
+  if (q0 < (unsigned)p.nq) stage(__ldg(cptr), img_base + img_off);
   float2 cnext = make_float2(0.f, 0.f);
   if (q0 + qstep < (unsigned)p.nq) cnext = __ldg(cptr + qstep);
   for (unsigned q = q0; q < (unsigned)p.nq; q += qstep) {
@@ -120,35 +121,39 @@ __global__ void __launch_bounds__(256, 4) corr_lookup_win_kernel(const LookupPar
     }
     __syncwarp();
     // ---- stage the next item: its loads are in flight while this one's taps are evaluated ----
-    const float* img_cur = img;
+    const unsigned img_cur = img_off;
+    img_off += img_step;
     if (q + qstep < (unsigned)p.nq) {
       const float2 c = cnext;
       cptr += qstep;
       if (q + 2 * qstep < (unsigned)p.nq) cnext = __ldg(cptr + qstep);
-      stage(c, img + img_step);
+      stage(c, img_base + img_off);
     }
     // ---- taps of the current item ----
     if (ok) {
       if (a < S) {
-        const float4 sx = ax[a];                                    // (w1, w0, off0, off1)
-        const float* w0p = win + __float_as_int(sx.z);
-        const float* w1p = win + __float_as_int(sx.w);
+        const float4 sx = ax[a];                                    // (w1, w0, byte off0, byte off1)
+        const char* w0p = reinterpret_cast<const char*>(win) + __float_as_int(sx.z);
+        const char* w1p = reinterpret_cast<const char*>(win) + __float_as_int(sx.w);
+        __half* ohq = kHalf ? p.out_hi + o_off + t0 : nullptr;
+        __half* olq = kHalf ? p.out_lo + o_off + t0 : nullptr;
+        float* oq = kHalf ? nullptr : p.out + o_off + t0;
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
           if (S % 3 == 0 || bq + 3 * j < S) {
             const float4 sy = ax[16 + bq + 3 * j];
             const int oy0 = __float_as_int(sy.z), oy1 = __float_as_int(sy.w);
-            float v = __fmul_rn(__fmul_rn(sy.x, sx.x), w0p[oy0]);   // corr.py:68, left to right
-            v = __fadd_rn(v, __fmul_rn(__fmul_rn(sy.x, sx.y), w1p[oy0]));
-            v = __fadd_rn(v, __fmul_rn(__fmul_rn(sy.y, sx.x), w0p[oy1]));
-            v = __fadd_rn(v, __fmul_rn(__fmul_rn(sy.y, sx.y), w1p[oy1]));
+            float v = __fmul_rn(__fmul_rn(sy.x, sx.x), *reinterpret_cast<const float*>(w0p + oy0));   // corr.py:68, left to right
+            v = __fadd_rn(v, __fmul_rn(__fmul_rn(sy.x, sx.y), *reinterpret_cast<const float*>(w1p + oy0)));
+            v = __fadd_rn(v, __fmul_rn(__fmul_rn(sy.y, sx.x), *reinterpret_cast<const float*>(w0p + oy1)));
+            v = __fadd_rn(v, __fmul_rn(__fmul_rn(sy.y, sx.y), *reinterpret_cast<const float*>(w1p + oy1)));
             if constexpr (kHalf) {
               __half hh, ll;
               split_f16(v, hh, ll);
-              oh[t0 + 3 * j] = hh;
-              ol[t0 + 3 * j] = ll;
+              ohq[3 * j] = hh;
+              olq[3 * j] = ll;
             } else {
-              o[t0 + 3 * j] = v;
+              oq[3 * j] = v;
             }
           }
         }
@@ -156,29 +161,25 @@ __global__ void __launch_bounds__(256, 4) corr_lookup_win_kernel(const LookupPar
     } else {                                                        // escape: gather per tap (never taken in practice)
       for (int t = lane; t < NT; t += 32) {
         const int ta = t / S, tb = t - ta * S;
-        const float v = sample_floor_ceil(img_cur, H, W, __fadd_rn(ecx, (float)(ta - R)), __fadd_rn(ecy, (float)(tb - R)));
+        const float v = sample_floor_ceil(img_base + img_cur, H, W, __fadd_rn(ecx, (float)(ta - R)), __fadd_rn(ecy, (float)(tb - R)));
         if constexpr (kHalf) {
           __half hh, ll;
           split_f16(v, hh, ll);
-          oh[t] = hh;
-          ol[t] = ll;
+          p.out_hi[o_off + t] = hh;
+          p.out_lo[o_off + t] = ll;
         } else {
-          o[t] = v;
+          p.out[o_off + t] = v;
         }
       }
     }
     if constexpr (kHalf) {
       const __half zero = __float2half_rn(0.f);
       for (int cpad = NT + lane; cpad < NT + npad; cpad += 32) {    // channels [levels * ntap, h_pad) of the operand planes
-        oh[cpad] = zero;
-        ol[cpad] = zero;
+        p.out_hi[o_off + cpad] = zero;
+        p.out_lo[o_off + cpad] = zero;
       }
-      oh += o_step;
-      ol += o_step;
-    } else {
-      o += o_step;
     }
-    img += img_step;
+    o_off += o_step;
   }
 }
 
@@ -186,6 +187,8 @@ __global__ void __launch_bounds__(256, 4) corr_lookup_win_kernel(const LookupPar
 inline bool lookup_win_launch(const LookupParams& p, int levels, int radius, cudaStream_t st) {
   const size_t nwork = (size_t)p.nq * levels;
   if (levels != 4 || (radius != 4 && radius != 3) || nwork >= (1u << 31)) return false;
+  if ((size_t)p.nq * p.lh[0] * p.lw[0] >= (1u << 31) || (size_t)p.nq * (size_t)(p.out_hi ? p.h_stride : p.out_stride) >= (1u << 31))
+    return false;                                                    // 32-bit element offsets inside the kernel
   bool vec = true;                                                  // 128-bit loads need 16-byte aligned rows on every level
   for (int l = 0; l < levels; ++l)
     vec = vec && (p.lw[l] % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.pyr[l]) & 15) == 0);

@@ -132,7 +132,7 @@ static int corr_build_tc(const float* f1, const float* f2, int B, int h, int w, 
   int lh = h, lw = w;
   for (int l = 0; l < levels; ++l) {
     const int N2 = lh * lw;
-    const int ntn = ceil_div(N2, 256);
+    const int ntn = ceil_div(N2, kCorrBn);
     const int bn = round_up(ceil_div(N2, ntn), 16);
     // B: level-l features [B][N2][C] -> the batch index rides in the "tap" coordinate
     RAFT_TRY(make_tmap_wgt2(&p.b_map[l], W.f2_hi[l], W.f2_lo[l], B, N2, C, bn));

@@ -215,11 +215,11 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-// Same, for an operand whose first row is `row_shift` (0..7) rows of 128 B past a 1024-byte boundary: the matrix base
-// offset field [49,52) = (start address >> 7) & 7 tells the swizzle which row phase the first row has.
-__device__ __forceinline__ uint64_t make_desc_sw128_shifted(uint32_t smem_addr, uint32_t base_offset) {
-  return make_desc_sw128(smem_addr) | ((uint64_t)(base_offset & 7u) << 49);
-}
+// An operand may start `r` rows (r * 128 bytes) past a 1024-byte boundary of a TMA-written swizzled tile -- the kRow3
+// convolution reads the same 136-pixel activation row at 0 / 1 / 2 pixels offset.  MEASURED on B200 (round 2,
+// profiles/r02_row3_descriptor_ab.txt): the start address alone is right; the tensor core derives the swizzle phase from the
+// address bits, and additionally setting the descriptor's "matrix base offset" field [49,52) to (address >> 7) & 7 -- what the
+// PTX text suggests for unaligned starts -- gives wrong products.
 // kind::f16 instruction descriptor: D=f32 (bits 4-5 = 1), A=B=f16 (0), both K-major, N>>3 at
 // [17,23), M>>4 at [24,29).
 __device__ __forceinline__ uint32_t make_idesc_f16(int m, int n) {

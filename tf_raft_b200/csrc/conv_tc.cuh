@@ -78,7 +78,6 @@ struct alignas(64) TcConvParams {
   // three taps; tap dx issues its MMAs on the activation rows [dx, dx + 128) through a descriptor whose start is shifted by
   // dx * 128 bytes.  3 + 3 boxes per 64-channel chunk instead of 9 + 9: these layers are bound by TMA box delivery.
   int row3;
-  int row3_base_mode;      // 1: shifted descriptors carry base_offset = dx (PTX matrix-descriptor rule); 0: base_offset 0
   // EPI_LINEAR with n_total == 2 (flow_head.conv2) inside the iteration loop: coords1 += delta_flow and
   // flow = coords1 - coords0 (model.py:102, :97) are applied by the thread that holds the pixel's two output columns.
   float* adv_coords;                       // (px, 2) coords1, updated in place; null = no fused advance
@@ -466,9 +465,8 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarpsConv, 1) conv_tc_kernel(con
               // stage = [A hi: 136 rows | A lo: 136 rows | W hi: tap 0, 1, 2 | W lo: tap 0, 1, 2]
 #pragma unroll 1
               for (int dx = 0; dx < 3; ++dx) {
-                const uint32_t bo = p.row3_base_mode ? (uint32_t)dx : 0u;
-                const uint64_t a_hi = make_desc_sw128_shifted(sa + dx * 128, bo);
-                const uint64_t a_lo = make_desc_sw128_shifted(sa + kARow3Bytes / 2 + dx * 128, bo);
+                const uint64_t a_hi = make_desc_sw128(sa + dx * 128);     // shifted start, base-offset field 0 (common.cuh)
+                const uint64_t a_lo = make_desc_sw128(sa + kARow3Bytes / 2 + dx * 128);
                 const uint64_t b_hi = make_desc_sw128(sa + kARow3Bytes + dx * b_bytes);
                 const uint64_t b_lo = make_desc_sw128(sa + kARow3Bytes + (3 + dx) * b_bytes);
 #pragma unroll

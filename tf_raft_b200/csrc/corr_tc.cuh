@@ -5,29 +5,32 @@
 //                                                                                       features are pooled, not the volume)
 // plus one preparation kernel that pools fmap2 and splits both feature maps into the fp16 (hi, lo) operand planes.
 //
-// Tile = 128 queries x bn targets (bn <= 256), K = C in 64-channel chunks, three fp16 passes per chunk (hi*hi, lo*hi,
-// hi*lo; fp32-grade), accumulation in TMEM with an IEEE-fp32 promotion into registers every two
-// chunks (24-MMA chains, exactly the arithmetic of every other tensor-core layer; a single 48-MMA chain per tile was tried
-// -- it is inside the pyramid tolerance, but its ~1e-6 relative difference moved one query of the benchmark pair across a
-// discontinuity of the reference sampler at iteration 4).
-// Warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..17 = promotion + store: each store warp owns 32 queries
-// (its TMEM lane quarter) x 64 columns, transposes 32 x 16 blocks through a swizzled 2 KB shared-memory patch and
-// writes 64-byte row segments (8 rows per store instruction).  The tile list runs over all levels (level 0 first), consecutive CTAs
-// take consecutive query tiles of the same target tile, so the target features are shared through L2.
-// Everything in the store path is inlined and register-resident: the round-1 form of this epilogue lived in a
-// non-inlined routine whose call made ptxas spill accumulators to local memory (which, with 227 KB of the L1/shared
-// array configured as shared memory, is an L2 round trip per access).
+// Tile = 128 queries x bn <= 128 targets, K = C in 64-channel chunks of a 3-stage ring (64 KB stages), three fp16 passes
+// per chunk (hi*hi, lo*hi, hi*lo; fp32-grade).  Accumulation chains are 24 MMAs long, exactly the
+// arithmetic of every other tensor-core layer: the K chunks are issued in groups of two, each group into its OWN 128-column
+// TMEM buffer, and the store warps add the group results in IEEE fp32 when they read them out ((0 + g0) + g1 + ...).  Four
+// TMEM buffers = two tiles in flight, so the MMAs of tile i+1 run while tile i is read out and stored.  (A single 48-MMA
+// chain per tile is inside the pyramid tolerance, but its ~1e-6 relative difference moved one query of the benchmark pair
+// across a discontinuity of the reference sampler at iteration 4 -- DESIGN.md section 4 -- so the chains stay at 24.)
+// Warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..9 = read-out + store: each store warp owns 32 queries (its TMEM lane
+// quarter) x 64 columns, transposes 32 x 32 blocks through a swizzled 4 KB shared-memory patch and writes full 128-byte
+// lines of the pyramid rows.  The tile list runs over all levels (level 0 first), consecutive CTAs take consecutive query
+// tiles of the same target tile, so the target features are shared through L2.  Everything in the store path is inlined
+// and register-resident: the round-1 form of this epilogue lived in a non-inlined routine whose call made ptxas spill
+// accumulators to local memory (which, with 227 KB of the L1/shared array configured as shared memory, is an L2 round trip
+// per access).
 #pragma once
 #include "conv_tc.cuh"
 #include "kernels.cuh"
 
 namespace raft {
 
-constexpr int kCorrStoreWarps = 16;
+constexpr int kCorrStoreWarps = 8;
 constexpr int kCorrThreads = 64 + 32 * kCorrStoreWarps;
-constexpr int kCorrStageBytes = 2 * kABytes + 2 * 256 * kChunkK * 2;     // 96 KB: A (hi|lo) 32 KB + B (hi|lo) up to 64 KB
-constexpr int kCorrStages = 2;
-constexpr int kCorrPatchBytes = kCorrStoreWarps * 2048;
+constexpr int kCorrBn = 128;                                              // target columns per tile (one TMEM buffer)
+constexpr int kCorrStageBytes = 2 * kABytes + 2 * kCorrBn * kChunkK * 2;  // 64 KB: A (hi|lo) 32 KB + B (hi|lo) up to 32 KB
+constexpr int kCorrStages = 3;
+constexpr int kCorrPatchBytes = kCorrStoreWarps * 4096;
 constexpr int kCorrSmemBytes = 1024 /*align slack*/ + kCorrStages * kCorrStageBytes + kCorrPatchBytes + 256 /*barriers*/;
 static_assert(kCorrSmemBytes <= 227 * 1024, "correlation kernel shared memory");
 
@@ -51,14 +54,15 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_tc_kernel(const __grid_c
   float* patches = reinterpret_cast<float*>(smem + kCorrStages * kCorrStageBytes);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kCorrStages * kCorrStageBytes + kCorrPatchBytes);
   uint64_t* empty_bar = full_bar + kCorrStages;
-  uint64_t* acc_full = empty_bar + kCorrStages;      // [2] issuer -> store warps
-  uint64_t* acc_empty = acc_full + 2;                // [2] store warps -> issuer
+  uint64_t* acc_full = empty_bar + kCorrStages;      // [2] issuer -> store warps: the buffer PAIR of a tile holds two groups
+  uint64_t* acc_empty = acc_full + 2;                // [2] store warps -> issuer: the pair has been read out
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mtiles = p.B * p.mtiles_img;
   const int ntiles = p.tile0[p.levels];
   const int chunks = p.chunks;
+  const int npairs = (chunks + 3) >> 2;              // group pairs (4 K chunks) per tile: 1 for C <= 256
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kCorrStages; ++s) {
@@ -113,8 +117,7 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_tc_kernel(const __grid_c
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    int it = 0, gg = 0;
-    const int ngroups = (chunks + 1) >> 1;             // promotion groups of two K chunks
+    int it = 0, uu = 0;                                // uu: uses of the buffer pairs (tile * npairs + pair)
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
       int l, nt, mt;
       decode(t, l, nt, mt);
@@ -122,14 +125,16 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_tc_kernel(const __grid_c
       const uint32_t idesc = make_idesc_f16(kTileM, bn);
       const uint32_t b_lo_off = (uint32_t)(bn * kChunkK * 2);
       int done = 0;
-      for (int g = 0; g < ngroups; ++g, ++gg) {
-        const int buf = gg & 1;
-        mbar_wait(&acc_empty[buf], ((uint32_t)(gg >> 1) & 1u) ^ 1u);       // promotion warps drained this buffer
+      for (int gp = 0; gp < npairs; ++gp, ++uu) {
+        const int pr = uu & 1;                         // buffer pair: TMEM columns [256 pr, 256 pr + 256)
+        mbar_wait(&acc_empty[pr], ((uint32_t)(uu >> 1) & 1u) ^ 1u);          // store warps have read this pair out
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 256);
-        const int gend = min(chunks, done + 2);
-        for (int first = 1; done < gend; ++done, ++it, first = 0) {
+        const int pend = min(chunks, done + 4);
+        for (; done < pend; ++done, ++it) {
           const int s = it % kCorrStages;
+          const int g = (done >> 1) & 1;               // group inside the pair: chunks {0,1} -> buffer 0, {2,3} -> buffer 1
+          const uint32_t d_tmem = tmem_base + (uint32_t)(pr * 256 + g * 128);
+          const bool first = (done & 1) == 0;
           mbar_wait(&full_bar[s], (uint32_t)(it / kCorrStages) & 1u);
           tc_fence_after();
           if (p.dbg && blockIdx.x == 0 && it < 512 && lane == 0) p.dbg[512 + it] = clock64();
@@ -144,28 +149,27 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_tc_kernel(const __grid_c
 #pragma unroll
             for (int k = 0; k < kChunkK / 16; ++k) umma_f16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
             umma_commit(&empty_bar[s]);
-            if (done == gend - 1) umma_commit(&acc_full[buf]);
+            if (done == pend - 1) umma_commit(&acc_full[pr]);
           }
           __syncwarp();
         }
       }
     }
   } else {
-    // ===================== promotion + store (warps 2..17) =====================
+    // ===================== read-out + store (warps 2..9) =====================
     const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
     const int part = (warp - 2) >> 2;                // columns [part * 64, part * 64 + 64) of the tile
     const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(part * 64);
-    float4* patch4 = reinterpret_cast<float4*>(patches + (warp - 2) * 512);
-    const int c4 = lane & 3, r8 = lane >> 2;
-    const int wsw = (lane >> 1) & 3, rsw = (lane >> 3) & 3;   // XOR swizzles: conflict-free 16-byte writes and reads
-    const int ngroups = (chunks + 1) >> 1;
-    int gg = 0, tt = 0;
+    float* patch = patches + (warp - 2) * 1024;
+    const int rsub = lane >> 3, q4 = lane & 7;
+    int uu = 0, tt = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tt) {
       int l, nt, mt;
       decode(t, l, nt, mt);
       const int bn = p.bn[l], n2 = p.n2[l];
+      const int b = mt / p.mtiles_img, m0 = (mt - b * p.mtiles_img) * kTileM, n0 = nt * bn;
       // 32-column blocks of this warp in this tile that hold columns of the level (warp-uniform)
-      const int nblk = max(0, min(2, (min(bn, n2 - nt * bn) - part * 64 + 31) >> 5));
+      const int nblk = max(0, min(2, (min(bn, n2 - n0) - part * 64 + 31) >> 5));
 
       float racc[2][32];
 #pragma unroll
@@ -174,69 +178,75 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_tc_kernel(const __grid_c
         for (int j = 0; j < 32; ++j) racc[ci][j] = 0.0f;
 
 #pragma unroll 1
-      for (int g = 0; g < ngroups; ++g, ++gg) {
-        const int buf = gg & 1;
-        mbar_wait(&acc_full[buf], (uint32_t)(gg >> 1) & 1u);
+      for (int gp = 0; gp < npairs; ++gp, ++uu) {
+        const int pr = uu & 1;
+        const int ng = min(2, ((chunks - 4 * gp) + 1) >> 1);               // groups in this pair (1 or 2)
+        mbar_wait(&acc_full[pr], (uint32_t)(uu >> 1) & 1u);
         tc_fence_after();
-        if (p.dbg && blockIdx.x == 0 && g == ngroups - 1 && tt < 256 && warp == 2 && lane == 0) p.dbg[1024 + tt] = clock64();
+        if (p.dbg && blockIdx.x == 0 && gp == npairs - 1 && tt < 256 && warp == 2 && lane == 0) p.dbg[1024 + tt] = clock64();
 #pragma unroll
-        for (int ci = 0; ci < 2; ++ci) {
-          if (ci < nblk) {
+        for (int g = 0; g < 2; ++g) {
+          if (g < ng) {
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              uint32_t r[16];
-              tmem_ld_32x16(trow + (uint32_t)(buf * 256 + ci * 32 + hh * 16), r);
-              tmem_ld_wait();
+            for (int ci = 0; ci < 2; ++ci) {
+              if (ci < nblk) {
+                uint32_t r[32];
+                tmem_ld_32x32(trow + (uint32_t)(pr * 256 + g * 128 + ci * 32), r);
+                tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < 16; ++j) racc[ci][hh * 16 + j] += __uint_as_float(r[j]);   // IEEE fp32 promotion
+                for (int j = 0; j < 32; ++j) racc[ci][j] += __uint_as_float(r[j]);   // IEEE fp32 sum of the 24-MMA groups
+              }
             }
           }
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[buf]);
-        if (p.dbg && blockIdx.x == 0 && g == ngroups - 1 && tt < 256 && warp == 2 && lane == 0) p.dbg[1536 + tt] = clock64();
+        if (lane == 0) mbar_arrive(&acc_empty[pr]);                        // the issuer may reuse the pair
+        if (p.dbg && blockIdx.x == 0 && gp == npairs - 1 && tt < 256 && warp == 2 && lane == 0) p.dbg[1536 + tt] = clock64();
       }
 
-      // ---- store: the issuer is already accumulating the next tile ----
-      const int b = mt / p.mtiles_img, m0 = (mt - b * p.mtiles_img) * kTileM, n0 = nt * bn;
+      // ---- store (the issuer is already two tiles ahead at most) ----
       const int row_base = m0 + quarter * 32;                              // first query of this warp's 32 rows
+      float* dst0 = p.out[l] + ((size_t)b * p.N + row_base + rsub) * n2 + n0 + part * 64 + 4 * q4;
       const bool vec = (n2 & 3) == 0;
-      float* dst0 = p.out[l] + ((size_t)b * p.N + row_base + r8) * n2 + n0 + part * 64 + 4 * c4;
 #pragma unroll
       for (int ci = 0; ci < 2; ++ci) {
         if (ci < nblk) {
+          __syncwarp();                                                    // previous block's readers are done with the patch
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            const int col = n0 + part * 64 + ci * 32 + hh * 16 + 4 * c4;
-            __syncwarp();                                                  // previous block's readers are done with the patch
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float4 a4 = make_float4(racc[ci][hh * 16 + 4 * q], racc[ci][hh * 16 + 4 * q + 1], racc[ci][hh * 16 + 4 * q + 2],
-                                      racc[ci][hh * 16 + 4 * q + 3]);
-              if (p.corr_mul != 0.0f) {
-                a4.x *= p.corr_mul; a4.y *= p.corr_mul; a4.z *= p.corr_mul; a4.w *= p.corr_mul;
-              } else {
-                a4.x = __fdiv_rn(a4.x, p.corr_div); a4.y = __fdiv_rn(a4.y, p.corr_div);
-                a4.z = __fdiv_rn(a4.z, p.corr_div); a4.w = __fdiv_rn(a4.w, p.corr_div);
-              }
-              patch4[lane * 4 + (q ^ wsw)] = a4;                           // lane = row: 16 columns = 4 x 16 bytes
+          for (int qq = 0; qq < 8; ++qq) {
+            float4 a4 = make_float4(racc[ci][4 * qq], racc[ci][4 * qq + 1], racc[ci][4 * qq + 2], racc[ci][4 * qq + 3]);
+            if (p.corr_mul != 0.0f) {
+              a4.x *= p.corr_mul; a4.y *= p.corr_mul; a4.z *= p.corr_mul; a4.w *= p.corr_mul;
+            } else {
+              a4.x = __fdiv_rn(a4.x, p.corr_div); a4.y = __fdiv_rn(a4.y, p.corr_div);
+              a4.z = __fdiv_rn(a4.z, p.corr_div); a4.w = __fdiv_rn(a4.w, p.corr_div);
             }
-            __syncwarp();
-            float* dst = dst0 + ci * 32 + hh * 16;
+            *reinterpret_cast<float4*>(patch + lane * 32 + ((qq ^ (lane & 7)) << 2)) = a4;
+          }
+          __syncwarp();
+          const int col = n0 + part * 64 + ci * 32 + 4 * q4;
+          float* dst = dst0 + ci * 32;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {                                  // rows r8 + 8k, columns 4 c4 .. 4 c4 + 3
-              const float4 v = patch4[(r8 + 8 * k) * 4 + (c4 ^ rsw)];
-              const int row = row_base + r8 + 8 * k;
+          for (int i0 = 0; i0 < 8; i0 += 4) {                              // four 16-byte loads in flight, then four stores
+            float4 v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int rr = 4 * (i0 + i) + rsub;
+              v[i] = *reinterpret_cast<const float4*>(patch + rr * 32 + ((q4 ^ (rr & 7)) << 2));
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int row = row_base + 4 * (i0 + i) + rsub;
               if (row < p.N && col < n2) {
-                float* d = dst + (size_t)(8 * k) * n2;
+                float* d = dst + (size_t)(4 * (i0 + i)) * n2;
                 if (vec) {
-                  *reinterpret_cast<float4*>(d) = v;
+                  *reinterpret_cast<float4*>(d) = v[i];
                 } else {
-                  d[0] = v.x;
-                  if (col + 1 < n2) d[1] = v.y;
-                  if (col + 2 < n2) d[2] = v.z;
-                  if (col + 3 < n2) d[3] = v.w;
+                  d[0] = v[i].x;
+                  if (col + 1 < n2) d[1] = v[i].y;
+                  if (col + 2 < n2) d[2] = v[i].z;
+                  if (col + 3 < n2) d[3] = v[i].w;
                 }
               }
             }

@@ -219,8 +219,7 @@ inline int enc_conv_tc(const EncCtx& c, const EncConvSlot& cs, const EncNormSlot
   tc_pick_tile(Wout, Hout, &tw, &th);
   if (tw * stride > 256) tw = 128 / stride, th = 128 / tw;
   // Wide 3x3 stride-1 layers with few output channels (layer1 / layer2 of both encoders at >= 128 feature columns): one
-  // activation box and one weight box per kernel ROW (conv_tc.cuh kRow3).  RAFT_B200_ROW3=0 disables, =2 uses descriptors
-  // without the base-offset field (A/B of the descriptor rule).
+  // activation box and one weight box per kernel ROW (conv_tc.cuh kRow3).  RAFT_B200_ROW3=0 disables (A/B timing).
   static const int row3_flag = [] { const char* e = getenv("RAFT_B200_ROW3"); return e ? atoi(e) : 1; }();
   const bool row3 = row3_flag && cs.kh == 3 && cs.kw == 3 && stride == 1 && tw == kTileM && th == 1 && cs.cout_pad <= 96 &&
                     cs.cout_pad % 8 == 0;
@@ -229,7 +228,6 @@ inline int enc_conv_tc(const EncCtx& c, const EncConvSlot& cs, const EncNormSlot
     RAFT_TRY(make_tmap_wgt3(&p.b_map, reinterpret_cast<const __half*>(c.prep + cs.hi),
                             reinterpret_cast<const __half*>(c.prep + cs.lo), cs.kh * cs.kw, cs.cout_pad, cs.cin_pad, cs.cout_pad));
     p.row3 = 1;
-    p.row3_base_mode = row3_flag == 2 ? 0 : 1;
   } else {
     RAFT_TRY(make_tmap_act2(&p.a_map[0], ahi, alo, c.N, Hin, Win, cs.cin_pad, tw, th, stride));
     RAFT_TRY(make_tmap_wgt2(&p.b_map, reinterpret_cast<const __half*>(c.prep + cs.hi),

@@ -208,7 +208,9 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_tc_kernel(const __grid_c
       // ---- store (the issuer is already two tiles ahead at most) ----
       const int row_base = m0 + quarter * 32;                              // first query of this warp's 32 rows
       float* dst0 = p.out[l] + ((size_t)b * p.N + row_base + rsub) * n2 + n0 + part * 64 + 4 * q4;
-      const bool vec = (n2 & 3) == 0;
+      const int col_end = min(n2, n0 + bn);                                // bn need not be a multiple of 32: the last block
+                                                                           // of a tile stops at the tile's own last column
+      const bool vec = (n2 & 3) == 0 && (bn & 3) == 0;
 #pragma unroll
       for (int ci = 0; ci < 2; ++ci) {
         if (ci < nblk) {
@@ -238,15 +240,15 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_tc_kernel(const __grid_c
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int row = row_base + 4 * (i0 + i) + rsub;
-              if (row < p.N && col < n2) {
+              if (row < p.N && col < col_end) {
                 float* d = dst + (size_t)(4 * (i0 + i)) * n2;
                 if (vec) {
                   *reinterpret_cast<float4*>(d) = v[i];
                 } else {
                   d[0] = v[i].x;
-                  if (col + 1 < n2) d[1] = v[i].y;
-                  if (col + 2 < n2) d[2] = v[i].z;
-                  if (col + 3 < n2) d[3] = v[i].w;
+                  if (col + 1 < col_end) d[1] = v[i].y;
+                  if (col + 2 < col_end) d[2] = v[i].z;
+                  if (col + 3 < col_end) d[3] = v[i].w;
                 }
               }
             }

@@ -228,6 +228,12 @@ inline int enc_conv_tc(const EncCtx& c, const EncConvSlot& cs, const EncNormSlot
     RAFT_TRY(make_tmap_wgt3(&p.b_map, reinterpret_cast<const __half*>(c.prep + cs.hi),
                             reinterpret_cast<const __half*>(c.prep + cs.lo), cs.kh * cs.kw, cs.cout_pad, cs.cin_pad, cs.cout_pad));
     p.row3 = 1;
+    // cin = cout = 64 (layer1): the nine taps stay resident in shared memory.  RAFT_B200_ROW3=2 keeps them streamed (A/B).
+    if (row3_flag != 2 && cs.cin_pad == 64 && cs.cout_pad == 64) {
+      RAFT_TRY(make_tmap_wgt3(&p.bres_map, reinterpret_cast<const __half*>(c.prep + cs.hi),
+                              reinterpret_cast<const __half*>(c.prep + cs.lo), cs.kh * cs.kw, cs.cout_pad, cs.cin_pad, cs.cout_pad, 9));
+      p.row3_wres = 1;
+    }
   } else {
     RAFT_TRY(make_tmap_act2(&p.a_map[0], ahi, alo, c.N, Hin, Win, cs.cin_pad, tw, th, stride));
     RAFT_TRY(make_tmap_wgt2(&p.b_map, reinterpret_cast<const __half*>(c.prep + cs.hi),

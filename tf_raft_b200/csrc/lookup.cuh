@@ -61,9 +61,16 @@ __global__ void __launch_bounds__(256, 4) corr_lookup_win_kernel(const LookupPar
   const int i = min(isy ? lane - S : lane, S - 1);
   const float fi = (float)(i - R), fmax_dim = (float)((isy ? H : W) - 1);
   const int t0 = a * S + bq;                                        // x-major tap order (corr.py:133-143): t = a * S + b
-  // window element k of this lane sits at (row, column) = (wrow(k), wcol(k)) of the footprint
+  // window element k of this lane sits at (row, column) = (wrow(k), wcol(k)) of the footprint: its global offset from the
+  // footprint origin and its shared-memory offset are per-lane constants of the level
   auto wrow = [&](int k) { const int e = lane + 32 * k; return kVec ? e >> 2 : e >> 4; };
   auto wcol = [&](int k) { const int e = lane + 32 * k; return kVec ? (e & 3) << 2 : e & 15; };
+  int goff[NV], soff[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    goff[k] = wrow(k) * W + wcol(k);
+    soff[k] = wrow(k) < kWinRows ? wrow(k) * kWinPitch + wcol(k) : -1;      // -1: this lane has no element k
+  }
 
   // Software pipeline: the set-up and the footprint LOADS of item n+1 are issued before the taps of item n are
   // evaluated, so every warp has one footprint in flight while it computes (the kernel is latency-bound otherwise:
@@ -93,11 +100,10 @@ __global__ void __launch_bounds__(256, 4) corr_lookup_win_kernel(const LookupPar
       const float* src = img_q + by * W + bxa;
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
-        const int r = wrow(k), cc = wcol(k);
-        if (r < kWinRows && by + r <= ey && bxa + cc <= ex) {
+        if (soff[k] >= 0 && wrow(k) <= ey - by && wcol(k) <= ex - bxa) {
           wmask |= 1u << k;
-          if constexpr (kVec) wv4[k] = __ldg(reinterpret_cast<const float4*>(src + r * W + cc));
-          else wv1[k] = __ldg(src + r * W + cc);
+          if constexpr (kVec) wv4[k] = __ldg(reinterpret_cast<const float4*>(src + goff[k]));
+          else wv1[k] = __ldg(src + goff[k]);
         }
       }
     }
@@ -115,8 +121,8 @@ __global__ void __launch_bounds__(256, 4) corr_lookup_win_kernel(const LookupPar
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
       if ((wmask >> k) & 1u) {
-        if constexpr (kVec) *reinterpret_cast<float4*>(win + wrow(k) * kWinPitch + wcol(k)) = wv4[k];
-        else win[wrow(k) * kWinPitch + wcol(k)] = wv1[k];
+        if constexpr (kVec) *reinterpret_cast<float4*>(win + soff[k]) = wv4[k];
+        else win[soff[k]] = wv1[k];
       }
     }
     __syncwarp();

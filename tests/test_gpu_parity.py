@@ -355,3 +355,24 @@ def test_graph_replay_survives_shape_changes(T):
         assert torch.equal(got, want), f'call {k} {bsz}x{H}x{W}'
         junk.append(torch.full((8 << 20,), float(k), device='cuda'))      # churn the allocator between calls
         del junk[:-1]
+
+
+def test_predict_stream_equals_synchronous_predict_step(T):
+    """bench.py's end-to-end leg goes through parallel.predict_stream (uploads, compute and read-backs of neighbouring
+    steps overlapped on three streams, double-buffered device inputs and staging, CUDA-graph replay): every result must be
+    bit-identical to a synchronous predict_step on the same pair, in order, with and without host-buffer reuse."""
+    from tf_raft_b200 import parallel
+    p = weights.init_params('raft', 7, bias_scale=0.02)
+    sync = T.RAFT(iters=3, iters_pred=3, precision='f16x2')
+    sync.load_params(p)
+    graph = T.RAFT(iters=3, iters_pred=3, precision='f16x2', use_graph=True)
+    graph.load_params(p)
+    pairs = [tuple(torch.from_numpy(a).pin_memory() for a in cases.images(2, 64, 96, 60 + k, 70 + k)) for k in range(5)]
+    want = [sync.predict_step((a.cuda(), b.cuda())).cpu() for a, b in pairs]
+    for reuse in (False, True):
+        got = []
+        for out in parallel.predict_stream(lambda a, b: graph.predict_step((a, b)), iter(pairs), torch.device('cuda'), reuse_host_buffers=reuse):
+            got.append(out.clone())                     # (a reused host buffer is only valid until two more results)
+        assert len(got) == len(want)
+        for k, (g, w) in enumerate(zip(got, want)):
+            assert torch.equal(g, w), f'pair {k}, reuse_host_buffers={reuse}'

@@ -78,11 +78,9 @@ struct alignas(64) TcConvParams {
   // three taps; tap dx issues its MMAs on the activation rows [dx, dx + 128) through a descriptor whose start is shifted by
   // dx * 128 bytes.  3 + 3 boxes per 64-channel chunk instead of 9 + 9: these layers are bound by TMA box delivery.
   int row3;
-  // kRow3 with RESIDENT weights (cin = cout = 64: layer1 of both encoders): all nine taps (hi + lo, 144 KB) are fetched once
-  // per CTA by one box and stay in shared memory beside two activation stages; a tile then loads three 34 KB activation
-  // boxes only and the mainloop is bound by the tensor pipe instead of TMA delivery.
-  int row3_wres;
-  CUtensorMap bres_map;    // (cin_pad, cout_pad, 9 taps, plane), box {64, bn, 9, 2}
+  // 1: the producer prefetches the activation boxes of this CTA's NEXT tile into L2 while it loads the current one (layers
+  // whose activations stream from HBM: the encoders at batch >= 4; off for the L2-resident update block).
+  int l2_prefetch;
   // EPI_LINEAR with n_total == 2 (flow_head.conv2) inside the iteration loop: coords1 += delta_flow and
   // flow = coords1 - coords0 (model.py:102, :97) are applied by the thread that holds the pixel's two output columns.
   float* adv_coords;                       // (px, 2) coords1, updated in place; null = no fused advance
@@ -329,14 +327,12 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarpsConv, 1) conv_tc_kernel(con
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nst = p.nstages;
   const int b_bytes = p.bn * kChunkK * 2;
-  const int wres_bytes = (kRow3 && p.row3_wres) ? 9 * 2 * b_bytes : 0;   // resident weights in front of the ring
-  uint8_t* stages = smem + wres_bytes;                        // ring of nst stages
+  uint8_t* stages = smem;                                     // ring of nst stages
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(stages + (size_t)nst * p.stage_bytes);
   uint64_t* empty_bar = full_bar + nst;
   uint64_t* acc_full = empty_bar + nst;      // [2] issuer -> promotion warps
   uint64_t* acc_empty = acc_full + 2;        // [2] promotion warps -> issuer
-  uint64_t* wres_bar = acc_empty + 2;        // resident weights landed
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(wres_bar + 1);
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float* patches = reinterpret_cast<float*>(stages + (size_t)nst * p.stage_bytes + 256);   // transposition patches (GRU q)
 
   const int warp = threadIdx.x >> 5;
@@ -363,7 +359,6 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarpsConv, 1) conv_tc_kernel(con
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], 4 * ((nchunks32 + chunks_per_part - 1) / chunks_per_part));   // one arrival per participating warp
     }
-    mbar_init(wres_bar, 1);
     fence_mbar_init();
     prefetch_tmap(&p.a_map[0]);
     prefetch_tmap(&p.b_map);
@@ -414,11 +409,19 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarpsConv, 1) conv_tc_kernel(con
         const int ty = mt % p.tiles_y;
         const int b = mt / p.tiles_y;
         const int x0 = tx * p.TW * p.stride, y0 = ty * p.TH * p.stride, n0 = nt * p.bn;
+        if (p.l2_prefetch && t + (int)gridDim.x < ntiles) {          // next tile of this CTA: rows y-1 .. y+TH, all chunks
+          const int t2 = t + (int)gridDim.x;
+          int mt2 = t2 % mtiles;
+          const int tx2 = mt2 % p.tiles_x;
+          mt2 /= p.tiles_x;
+          const int ty2 = mt2 % p.tiles_y, b2 = mt2 / p.tiles_y;
+          const int px0 = tx2 * p.TW * p.stride - (kRow3 ? p.pw : 0), py0 = ty2 * p.TH * p.stride;
+          for (int ky = 0; ky < p.kh; ++ky)
+            for (int seg = 0; seg < p.nseg; ++seg)
+              for (int ch = 0; ch < p.seg_chunks[seg]; ++ch)
+                tma_prefetch_5d(&p.a_map[seg], p.seg_c0[seg] + ch * kChunkK, px0, py0 + ky - p.ph, b2, 0);
+        }
         if constexpr (kRow3) {
-          if (p.row3_wres && t == (int)blockIdx.x) {          // first tile of this CTA: fetch the layer's weights once
-            mbar_arrive_expect_tx(wres_bar, (uint32_t)wres_bytes);
-            tma_load_4d(smem, &p.bres_map, wres_bar, 0, n0, 0, 0);
-          }
           for (int ky = 0; ky < p.kh; ++ky) {
             for (int ch = 0; ch < p.seg_chunks[0]; ++ch, ++it) {
               const int s = it % nst;
@@ -427,26 +430,26 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarpsConv, 1) conv_tc_kernel(con
               uint8_t* st = stages + (size_t)s * p.stage_bytes;
               mbar_arrive_expect_tx(&full_bar[s], (uint32_t)p.stage_bytes);
               tma_load_5d(st, &p.a_map[0], &full_bar[s], p.seg_c0[0] + ch * kChunkK, x0 - p.pw, y0 + ky - p.ph, b, 0);
-              if (!p.row3_wres) tma_load_4d(st + kARow3Bytes, &p.b_map, &full_bar[s], ch * kChunkK, n0, ky * p.kw, 0);
+              tma_load_4d(st + kARow3Bytes, &p.b_map, &full_bar[s], ch * kChunkK, n0, ky * p.kw, 0);
             }
           }
-          continue;
-        }
-        for (int tap = 0; tap < ntaps; ++tap) {
-          const int dy = tap / p.kw - p.ph, dx = tap % p.kw - p.pw;
-          int kc = 0;
-          for (int seg = 0; seg < p.nseg; ++seg) {
-            for (int ch = 0; ch < p.seg_chunks[seg]; ++ch, ++kc, ++it) {
-              const int s = it % nst;
-              const uint32_t phase = (uint32_t)(it / nst) & 1u;
-              mbar_wait(&empty_bar[s], phase ^ 1u);
-              if (p.dbg && blockIdx.x == 0 && it < 512) p.dbg[it] = clock64();              // slot free
-              uint8_t* st = stages + (size_t)s * p.stage_bytes;
-              if (it >= npre) mbar_arrive_expect_tx(&full_bar[s], (uint32_t)p.stage_bytes);
-              const int c = p.seg_c0[seg] + ch * kChunkK;
-              // two boxes per stage: [A_hi | A_lo] and [B_hi | B_lo] (TMA cost is per box, not per byte)
-              tma_load_5d(st, &p.a_map[seg], &full_bar[s], c, x0 + dx, y0 + dy, b, 0);
-              if (it >= npre) tma_load_4d(st + 2 * kABytes, &p.b_map, &full_bar[s], kc * kChunkK, n0, tap, 0);
+        } else {
+          for (int tap = 0; tap < ntaps; ++tap) {
+            const int dy = tap / p.kw - p.ph, dx = tap % p.kw - p.pw;
+            int kc = 0;
+            for (int seg = 0; seg < p.nseg; ++seg) {
+              for (int ch = 0; ch < p.seg_chunks[seg]; ++ch, ++kc, ++it) {
+                const int s = it % nst;
+                const uint32_t phase = (uint32_t)(it / nst) & 1u;
+                mbar_wait(&empty_bar[s], phase ^ 1u);
+                if (p.dbg && blockIdx.x == 0 && it < 512) p.dbg[it] = clock64();              // slot free
+                uint8_t* st = stages + (size_t)s * p.stage_bytes;
+                if (it >= npre) mbar_arrive_expect_tx(&full_bar[s], (uint32_t)p.stage_bytes);
+                const int c = p.seg_c0[seg] + ch * kChunkK;
+                // two boxes per stage: [A_hi | A_lo] and [B_hi | B_lo] (TMA cost is per box, not per byte)
+                tma_load_5d(st, &p.a_map[seg], &full_bar[s], c, x0 + dx, y0 + dy, b, 0);
+                if (it >= npre) tma_load_4d(st + 2 * kABytes, &p.b_map, &full_bar[s], kc * kChunkK, n0, tap, 0);
+              }
             }
           }
         }
@@ -456,10 +459,6 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarpsConv, 1) conv_tc_kernel(con
     // ===================== MMA issuer =====================
     const uint32_t idesc = make_idesc_f16(kTileM, p.bn);
     int it = 0, gg = 0;
-    if (kRow3 && p.row3_wres && (int)blockIdx.x < ntiles) {
-      mbar_wait(wres_bar, 0u);
-      tc_fence_after();
-    }
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
       int done = 0;
       for (int g = 0; g < ngroups; ++g, ++gg) {
@@ -483,10 +482,8 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarpsConv, 1) conv_tc_kernel(con
               for (int dx = 0; dx < 3; ++dx) {
                 const uint64_t a_hi = make_desc_sw128(sa + dx * 128);     // shifted start, base-offset field 0 (common.cuh)
                 const uint64_t a_lo = make_desc_sw128(sa + kARow3Bytes / 2 + dx * 128);
-                // weights: this stage's own box [hi: 3 taps | lo: 3 taps], or the resident set [hi: 9 taps | lo: 9 taps]
-                const uint32_t wb = p.row3_wres ? smem_u32(smem) + (uint32_t)((done % 3) * 3 + dx) * b_bytes : sa + kARow3Bytes + dx * b_bytes;
-                const uint64_t b_hi = make_desc_sw128(wb);
-                const uint64_t b_lo = make_desc_sw128(wb + (p.row3_wres ? 9 : 3) * b_bytes);
+                const uint64_t b_hi = make_desc_sw128(sa + kARow3Bytes + dx * b_bytes);
+                const uint64_t b_lo = make_desc_sw128(sa + kARow3Bytes + (3 + dx) * b_bytes);
 #pragma unroll
                 for (int k = 0; k < kChunkK / 16; ++k)
                   umma_f16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (!first || dx > 0 || k > 0) ? 1u : 0u);
@@ -662,17 +659,16 @@ inline int tc_finalize(TcConvParams& p) {
   p.tiles_x = ceil_div(p.W, p.TW);
   p.tiles_y = ceil_div(p.H, p.TH);
   p.stage_bytes = 2 * kABytes + 2 * p.bn * kChunkK * 2;
-  if (p.row3) p.stage_bytes = kARow3Bytes + (p.row3_wres ? 0 : 3 * 2 * p.bn * kChunkK * 2);
-  const int wres = (p.row3 && p.row3_wres) ? 9 * 2 * p.bn * kChunkK * 2 : 0;
+  if (p.row3) p.stage_bytes = kARow3Bytes + 3 * 2 * p.bn * kChunkK * 2;
   const int patch = tc_uses_patch(p.mode) ? kEpiPatchBytes : 0;   // 16 x 2 KB patches (GRU q)
-  int nst = (kSmemBudget - patch - wres) / p.stage_bytes;
+  int nst = (kSmemBudget - patch) / p.stage_bytes;
   if (nst > 8) nst = 8;
   p.nstages = nst;
   int cols = 32;
   while (cols < 2 * p.bn) cols <<= 1;           // two accumulator buffers (ping-pong promotion)
   p.tmem_cols = cols;
   if (p.group_chunks <= 0) p.group_chunks = 2;
-  return wres + nst * p.stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + patch;
+  return nst * p.stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/ + patch;
 }
 
 // RAFT_B200_PDL=0 disables programmatic dependent launch of the per-layer kernel (A/B timing).
@@ -704,7 +700,6 @@ inline int tc_launch(TcConvParams& p, int n_tiles_n, cudaStream_t stream) {
   const unsigned grid = (unsigned)(ntiles < kNumSMs ? ntiles : kNumSMs);   // one persistent CTA per SM
   p.pdl = tc_pdl_enabled() ? 1 : 0;
   const int threads = 64 + 32 * kEpiWarpsConv;
-  if (p.row3_wres && (!p.row3 || p.seg_chunks[0] != 1)) return RAFT_ERR_UNSUPPORTED;
   if (p.row3 && (p.mode != EPI_LINEAR || p.kh != 3 || p.kw != 3 || p.stride != 1 || p.TH != 1 || p.TW != kTileM || p.nseg != 1 ||
                  p.bn % 8 != 0 || n_tiles_n != 1))
     return RAFT_ERR_UNSUPPORTED;

@@ -228,12 +228,8 @@ inline int enc_conv_tc(const EncCtx& c, const EncConvSlot& cs, const EncNormSlot
     RAFT_TRY(make_tmap_wgt3(&p.b_map, reinterpret_cast<const __half*>(c.prep + cs.hi),
                             reinterpret_cast<const __half*>(c.prep + cs.lo), cs.kh * cs.kw, cs.cout_pad, cs.cin_pad, cs.cout_pad));
     p.row3 = 1;
-    // cin = cout = 64 (layer1): the nine taps stay resident in shared memory.  RAFT_B200_ROW3=2 keeps them streamed (A/B).
-    if (row3_flag != 2 && cs.cin_pad == 64 && cs.cout_pad == 64) {
-      RAFT_TRY(make_tmap_wgt3(&p.bres_map, reinterpret_cast<const __half*>(c.prep + cs.hi),
-                              reinterpret_cast<const __half*>(c.prep + cs.lo), cs.kh * cs.kw, cs.cout_pad, cs.cin_pad, cs.cout_pad, 9));
-      p.row3_wres = 1;
-    }
+    // (Keeping the nine taps of the 64-channel layers resident in shared memory was measured in round 2: slower, 489 vs 496
+    // pairs/s -- it leaves 68 KB of activation stages in flight against an HBM latency of ~3.1 k cycles.)
   } else {
     RAFT_TRY(make_tmap_act2(&p.a_map[0], ahi, alo, c.N, Hin, Win, cs.cin_pad, tw, th, stride));
     RAFT_TRY(make_tmap_wgt2(&p.b_map, reinterpret_cast<const __half*>(c.prep + cs.hi),
@@ -266,6 +262,11 @@ inline int enc_conv_tc(const EncCtx& c, const EncConvSlot& cs, const EncNormSlot
     p.residual = skip; p.res_stride = cs.cout; p.res_c0 = 0;
   } else {
     p.act = ACT_NONE; p.out_hi = nullptr; p.out_lo = nullptr;
+  }
+  {
+    // L2 prefetch one tile ahead (conv_tc.cuh): RAFT_B200_ENC_PREFETCH=0 disables (A/B timing).
+    static const int pf = [] { const char* e = getenv("RAFT_B200_ENC_PREFETCH"); return e ? atoi(e) : 1; }();
+    p.l2_prefetch = pf ? 1 : 0;
   }
   if (g_dbg_layer >= 1000 && g_dbg_count++ == g_dbg_layer - 1000) p.dbg = g_dbg_buf;   // timeline of the k-th encoder conv
   {

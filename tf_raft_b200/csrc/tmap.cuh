@@ -73,12 +73,12 @@ inline int make_tmap_wgt2(CUtensorMap* out, const __half* hi, const __half* lo, 
 
 // Weight planes, three taps (one kernel row) per box: box {64, bn, 3, 2} -> smem [hi: tap 0 | tap 1 | tap 2][lo: ...].
 inline int make_tmap_wgt3(CUtensorMap* out, const __half* hi, const __half* lo, int taps, int cout_pad, int cin_pad,
-                          int bn, int box_taps = 3) {
+                          int bn) {
   const ptrdiff_t pstride = reinterpret_cast<const char*>(lo) - reinterpret_cast<const char*>(hi);
   if (pstride <= 0 || (pstride & 15)) return RAFT_ERR_BAD_ARG;
   uint64_t dims[4] = {(uint64_t)cin_pad, (uint64_t)cout_pad, (uint64_t)taps, 2};
   uint64_t str[3] = {(uint64_t)cin_pad * 2, (uint64_t)cout_pad * cin_pad * 2, (uint64_t)pstride};
-  uint32_t box[4] = {64, (uint32_t)bn, (uint32_t)box_taps, 2};
+  uint32_t box[4] = {64, (uint32_t)bn, 3, 2};
   return make_tmap_f16(out, hi, 4, dims, str, box);
 }
 

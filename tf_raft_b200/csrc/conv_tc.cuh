@@ -78,9 +78,6 @@ struct alignas(64) TcConvParams {
   // three taps; tap dx issues its MMAs on the activation rows [dx, dx + 128) through a descriptor whose start is shifted by
   // dx * 128 bytes.  3 + 3 boxes per 64-channel chunk instead of 9 + 9: these layers are bound by TMA box delivery.
   int row3;
-  // 1: the producer prefetches the activation boxes of this CTA's NEXT tile into L2 while it loads the current one (layers
-  // whose activations stream from HBM: the encoders at batch >= 4; off for the L2-resident update block).
-  int l2_prefetch;
   // EPI_LINEAR with n_total == 2 (flow_head.conv2) inside the iteration loop: coords1 += delta_flow and
   // flow = coords1 - coords0 (model.py:102, :97) are applied by the thread that holds the pixel's two output columns.
   float* adv_coords;                       // (px, 2) coords1, updated in place; null = no fused advance
@@ -92,6 +89,18 @@ struct alignas(64) TcConvParams {
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+// 32-byte global store (STG.256, sm_100): the thread-per-row epilogues write a full 32-byte sector per lane and instruction
+// instead of half of one -- half as many store instructions and LSU wavefronts for the same bytes.  `p` must be 32-byte aligned.
+__device__ __forceinline__ void st8u(void* p, const uint32_t (&r)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+               "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void st8f(float* p, float a, float b, float c, float d, float e, float f, float g, float h) {
+  const uint32_t r[8] = {__float_as_uint(a), __float_as_uint(b), __float_as_uint(c), __float_as_uint(d),
+                         __float_as_uint(e), __float_as_uint(f), __float_as_uint(g), __float_as_uint(h)};
+  st8u(p, r);
+}
 // L2-coherent 16-byte load (ld.global.cg): z and h may have been written by another CTA of the SAME grid (update_mega_kernel),
 // so they must not be served from this SM's L1 nor through the non-coherent path.
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
@@ -168,7 +177,11 @@ __device__ __forceinline__ void tc_epilogue_regs(const TcConvParams& p, float (&
     if (p.out_f32) {
       const int nvalid = min(ncol, p.n_total - col);
       float* dst = p.out_f32 + pix * (size_t)p.f32_stride + p.f32_c0 + col;
-      if (nvalid == 32 && ((p.f32_stride | p.f32_c0) & 3) == 0) {
+      if (nvalid == 32 && ((p.f32_stride | p.f32_c0) & 7) == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          st8f(dst + 8 * q, v[8 * q], v[8 * q + 1], v[8 * q + 2], v[8 * q + 3], v[8 * q + 4], v[8 * q + 5], v[8 * q + 6], v[8 * q + 7]);
+      } else if (nvalid == 32 && ((p.f32_stride | p.f32_c0) & 3) == 0) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) st4(dst + 4 * q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
       } else {
@@ -193,10 +206,17 @@ __device__ __forceinline__ void tc_epilogue_regs(const TcConvParams& p, float (&
   } else if (MODE == EPI_GRU_ZR) {
     if (col < p.hid) {                                 // z gate -> fp32 plane
       float* dst = p.z + pix * (size_t)p.hid + col;
+      if ((p.hid & 7) == 0) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
-        st4(dst + 4 * q, make_float4(fast_sigmoid(v[4 * q]), fast_sigmoid(v[4 * q + 1]), fast_sigmoid(v[4 * q + 2]),
-                                     fast_sigmoid(v[4 * q + 3])));
+        for (int q = 0; q < 4; ++q)
+          st8f(dst + 8 * q, fast_sigmoid(v[8 * q]), fast_sigmoid(v[8 * q + 1]), fast_sigmoid(v[8 * q + 2]), fast_sigmoid(v[8 * q + 3]),
+               fast_sigmoid(v[8 * q + 4]), fast_sigmoid(v[8 * q + 5]), fast_sigmoid(v[8 * q + 6]), fast_sigmoid(v[8 * q + 7]));
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          st4(dst + 4 * q, make_float4(fast_sigmoid(v[4 * q]), fast_sigmoid(v[4 * q + 1]), fast_sigmoid(v[4 * q + 2]),
+                                       fast_sigmoid(v[4 * q + 3])));
+      }
     } else {                                           // r gate -> r*h, re-split for the q convolution
       const int hc = col - p.hid;
       const float* hp = p.h + pix * (size_t)p.hid + hc;
@@ -228,20 +248,30 @@ __device__ __forceinline__ void tc_epilogue_regs(const TcConvParams& p, float (&
     dlo = p.out_lo + o;
   }
 
-  if (dhi) {                                           // fp16 hi/lo re-split, 8 channels (16 bytes) per store
+  if (dhi) {                                           // fp16 hi/lo re-split, 16 channels (32 bytes) per store
+    // (operand planes: channel strides are multiples of 64 and slices start at multiples of 32 channels -> 32-byte aligned;
+    //  a slice that starts elsewhere takes the 16-byte form)
+    const bool wide = ((reinterpret_cast<uintptr_t>(dhi) | reinterpret_cast<uintptr_t>(dlo)) & 31) == 0;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      uint32_t ph[4], pl[4];
+    for (int q = 0; q < 2; ++q) {
+      uint32_t ph[8], pl[8];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
+      for (int e = 0; e < 8; ++e) {
         __half h0, l0, h1, l1;
-        split_f16(v[8 * q + 2 * e], h0, l0);
-        split_f16(v[8 * q + 2 * e + 1], h1, l1);
+        split_f16(v[16 * q + 2 * e], h0, l0);
+        split_f16(v[16 * q + 2 * e + 1], h1, l1);
         ph[e] = pack_h2(h0, h1);
         pl[e] = pack_h2(l0, l1);
       }
-      reinterpret_cast<uint4*>(dhi)[q] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-      reinterpret_cast<uint4*>(dlo)[q] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+      if (wide) {
+        st8u(dhi + 16 * q, ph);
+        st8u(dlo + 16 * q, pl);
+      } else {
+        reinterpret_cast<uint4*>(dhi)[2 * q] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+        reinterpret_cast<uint4*>(dhi)[2 * q + 1] = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+        reinterpret_cast<uint4*>(dlo)[2 * q] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+        reinterpret_cast<uint4*>(dlo)[2 * q + 1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+      }
     }
   }
 }
@@ -409,18 +439,6 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarpsConv, 1) conv_tc_kernel(con
         const int ty = mt % p.tiles_y;
         const int b = mt / p.tiles_y;
         const int x0 = tx * p.TW * p.stride, y0 = ty * p.TH * p.stride, n0 = nt * p.bn;
-        if (p.l2_prefetch && t + (int)gridDim.x < ntiles) {          // next tile of this CTA: rows y-1 .. y+TH, all chunks
-          const int t2 = t + (int)gridDim.x;
-          int mt2 = t2 % mtiles;
-          const int tx2 = mt2 % p.tiles_x;
-          mt2 /= p.tiles_x;
-          const int ty2 = mt2 % p.tiles_y, b2 = mt2 / p.tiles_y;
-          const int px0 = tx2 * p.TW * p.stride - (kRow3 ? p.pw : 0), py0 = ty2 * p.TH * p.stride;
-          for (int ky = 0; ky < p.kh; ++ky)
-            for (int seg = 0; seg < p.nseg; ++seg)
-              for (int ch = 0; ch < p.seg_chunks[seg]; ++ch)
-                tma_prefetch_5d(&p.a_map[seg], p.seg_c0[seg] + ch * kChunkK, px0, py0 + ky - p.ph, b2, 0);
-        }
         if constexpr (kRow3) {
           for (int ky = 0; ky < p.kh; ++ky) {
             for (int ch = 0; ch < p.seg_chunks[0]; ++ch, ++it) {

@@ -263,11 +263,8 @@ inline int enc_conv_tc(const EncCtx& c, const EncConvSlot& cs, const EncNormSlot
   } else {
     p.act = ACT_NONE; p.out_hi = nullptr; p.out_lo = nullptr;
   }
-  {
-    // L2 prefetch one tile ahead (conv_tc.cuh): RAFT_B200_ENC_PREFETCH=0 disables (A/B timing).
-    static const int pf = [] { const char* e = getenv("RAFT_B200_ENC_PREFETCH"); return e ? atoi(e) : 1; }();
-    p.l2_prefetch = pf ? 1 : 0;
-  }
+  // (An L2 tensor prefetch of the next tile's activation boxes was measured in round 2: no effect, 494 vs 496 pairs/s -- the
+  //  ~3 k-cycle load latency of these layers is TMA service time, not HBM latency; profiles/README.md.)
   if (g_dbg_layer >= 1000 && g_dbg_count++ == g_dbg_layer - 1000) p.dbg = g_dbg_buf;   // timeline of the k-th encoder conv
   {
     // Promotion group of the encoder convolutions: their contractions are short (K <= 1152, 18 chunks), so the fp32

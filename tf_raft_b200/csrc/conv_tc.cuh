@@ -96,6 +96,17 @@ __device__ __forceinline__ void st8u(void* p, const uint32_t (&r)[8]) {
                "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
+// 32-byte loads: L2-coherent (tensors another CTA of the same grid may have written) and read-only forms.
+__device__ __forceinline__ void ldcg8(const float* p, float (&r)[8]) {
+  asm volatile("ld.global.cg.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void ldnc8(const float* p, float (&r)[8]) {
+  asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
+               : "l"(p));
+}
 __device__ __forceinline__ void st8f(float* p, float a, float b, float c, float d, float e, float f, float g, float h) {
   const uint32_t r[8] = {__float_as_uint(a), __float_as_uint(b), __float_as_uint(c), __float_as_uint(d),
                          __float_as_uint(e), __float_as_uint(f), __float_as_uint(g), __float_as_uint(h)};
@@ -154,7 +165,15 @@ __device__ __forceinline__ void tc_epilogue_regs(const TcConvParams& p, float (&
     if (full) {
       if (p.residual) {
         const float* rp = p.residual + pix * (size_t)p.res_stride + p.res_c0 + col;
-        if (((p.res_stride | p.res_c0) & 3) == 0) {
+        if (((p.res_stride | p.res_c0) & 7) == 0) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float r8[8];
+            ldnc8(rp + 8 * q, r8);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[8 * q + e] = fmaxf(v[8 * q + e] + r8[e], 0.f);
+          }
+        } else if (((p.res_stride | p.res_c0) & 3) == 0) {
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const float4 r4 = ldg4(rp + 4 * q);
@@ -220,11 +239,21 @@ __device__ __forceinline__ void tc_epilogue_regs(const TcConvParams& p, float (&
     } else {                                           // r gate -> r*h, re-split for the q convolution
       const int hc = col - p.hid;
       const float* hp = p.h + pix * (size_t)p.hid + hc;
+      if ((p.hid & 7) == 0) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 hv = ldcg4(hp + 4 * q);
-        v[4 * q] = fast_sigmoid(v[4 * q]) * hv.x; v[4 * q + 1] = fast_sigmoid(v[4 * q + 1]) * hv.y;
-        v[4 * q + 2] = fast_sigmoid(v[4 * q + 2]) * hv.z; v[4 * q + 3] = fast_sigmoid(v[4 * q + 3]) * hv.w;
+        for (int q = 0; q < 4; ++q) {
+          float h8[8];
+          ldcg8(hp + 8 * q, h8);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[8 * q + e] = fast_sigmoid(v[8 * q + e]) * h8[e];
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 hv = ldcg4(hp + 4 * q);
+          v[4 * q] = fast_sigmoid(v[4 * q]) * hv.x; v[4 * q + 1] = fast_sigmoid(v[4 * q + 1]) * hv.y;
+          v[4 * q + 2] = fast_sigmoid(v[4 * q + 2]) * hv.z; v[4 * q + 3] = fast_sigmoid(v[4 * q + 3]) * hv.w;
+        }
       }
       const size_t o = pix * (size_t)p.h_stride + p.h_c0 + hc;
       dhi = p.out_hi + o;

@@ -589,12 +589,16 @@ __global__ void __launch_bounds__(256) norm_stats_kernel(const float* __restrict
     float* o = part + (((size_t)g * nsplit + sp) * 3) * C + c;
     o[0] = n; o[C] = mean; o[2 * C] = m2;
   }
-  __threadfence();                                       // this block's partials are visible before it is counted
   __syncthreads();
-  if (threadIdx.x == 0) is_last = atomicAdd(&counter[g], 1u) == (unsigned)(nsplit - 1);
+  if (threadIdx.x == 0) {
+    // One gpu-scope fence per block (cumulative over the block's partials through the barrier above) -- a fence in every
+    // thread cost +52 us per launch (profiles/r02_launches_trip11.txt).
+    __threadfence();
+    is_last = atomicAdd(&counter[g], 1u) == (unsigned)(nsplit - 1);
+    __threadfence();
+  }
   __syncthreads();
   if (is_last) {
-    __threadfence();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int cc = warp; cc < C; cc += 8) {
       norm_merge_channel(part, g, cc, C, nsplit, lane, n, mean, m2);

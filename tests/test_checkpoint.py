@@ -118,3 +118,114 @@ def test_key_mapping_examples():
     assert f('_CHECKPOINTABLE_OBJECT_GRAPH') is None
     assert f('optimizer/beta_1' + s) is None
     assert f('fnet/conv1/kernel/.OPTIMIZER_SLOT/optimizer/m' + s) is None
+
+
+# ---- hand-assembled index bytes (format description only; none of checkpoint.py's writer helpers) -----------------------
+def _crc32c_bitwise(data):
+    """Independent CRC-32C: bit-at-a-time over the reflected Castagnoli polynomial (no table)."""
+    crc = 0xFFFFFFFF
+    for byte in data:
+        crc ^= byte
+        for _ in range(8):
+            crc = (crc >> 1) ^ (0x82F63B78 if crc & 1 else 0)
+    return crc ^ 0xFFFFFFFF
+
+
+def _trailer(block):
+    """LevelDB block trailer: compression type 0 + masked crc32c of (block || type), little-endian."""
+    crc = _crc32c_bitwise(block + b'\x00')
+    masked = (((crc >> 15) | (crc << 17)) + 0xa282ead8) & 0xFFFFFFFF
+    return b'\x00' + masked.to_bytes(4, 'little')
+
+
+def test_reader_on_hand_assembled_table(tmp_path):
+    """An `.index` typed out byte by byte from the LevelDB table / tensor-bundle description: two data blocks, prefix
+    compression inside a block (shared > 0), a block with TWO restart points, a multi-byte varint offset, a string entry
+    the reader must skip, and the 48-byte footer.  Pins the reader against the format rather than against the writer."""
+    f32 = np.array([1.0, -2.5, 3.25], dtype='<f4')
+    i64 = np.array([[7, -1]], dtype='<i8')
+    pad = bytes(200)                                        # pushes the second tensor to offset 212 (two-byte varint)
+    data = f32.tobytes() + pad + i64.tobytes()
+    tensor_crc = lambda raw: ((((_crc32c_bitwise(raw) >> 15) | (_crc32c_bitwise(raw) << 17)) + 0xa282ead8) & 0xFFFFFFFF)
+
+    # BundleHeaderProto {num_shards: 1, version {producer: 1}}
+    header = bytes([0x08, 0x01, 0x1a, 0x02, 0x08, 0x01])
+    # BundleEntryProto {dtype: DT_FLOAT(1), shape {dim {size: 3}}, size: 12, crc32c: fixed32}   (offset 0 omitted)
+    e_f32 = bytes([0x08, 0x01, 0x12, 0x04, 0x12, 0x02, 0x08, 0x03, 0x28, 0x0c, 0x35]) + tensor_crc(f32.tobytes()).to_bytes(4, 'little')
+    # {dtype: DT_INT64(9), shape {dim {size: 1} dim {size: 2}}, offset: 212 = d4 01, size: 16, crc32c}
+    e_i64 = bytes([0x08, 0x09, 0x12, 0x08, 0x12, 0x02, 0x08, 0x01, 0x12, 0x02, 0x08, 0x02, 0x20, 0xd4, 0x01, 0x28, 0x10, 0x35]) \
+        + tensor_crc(i64.tobytes()).to_bytes(4, 'little')
+    # {dtype: DT_STRING(7), shape {}, size: 5}: not a numeric tensor, skipped by the reader
+    e_str = bytes([0x08, 0x07, 0x12, 0x00, 0x28, 0x05])
+
+    def entry(shared, suffix, value):
+        return bytes([shared, len(suffix), len(value)]) + suffix + value
+
+    # data block 0: keys "", "ab/w", "ab/x" (shares "ab/" with its predecessor); one restart at offset 0
+    b0 = entry(0, b'', header) + entry(0, b'ab/w', e_f32) + entry(3, b'x', e_str)
+    b0 += (0).to_bytes(4, 'little') + (1).to_bytes(4, 'little')
+    # data block 1: keys "cd/a", "cd/b" with a restart point at EACH (second entry therefore stores its key in full)
+    first = entry(0, b'cd/a', e_str)
+    b1 = first + entry(0, b'cd/b', e_i64)
+    b1 += (0).to_bytes(4, 'little') + len(first).to_bytes(4, 'little') + (2).to_bytes(4, 'little')
+    meta = (0).to_bytes(4, 'little') + (1).to_bytes(4, 'little')                 # empty metaindex block
+    off0 = 0
+    off1 = len(b0) + 5
+    off_meta = off1 + len(b1) + 5
+    off_index = off_meta + len(meta) + 5
+    assert max(off1, off_meta, off_index, len(b0), len(b1)) < 128 * 2            # handles below: one- or two-byte varints
+
+    def varint(v):
+        return bytes([v]) if v < 128 else bytes([(v & 0x7f) | 0x80, v >> 7])
+
+    # index block: separator key (>= last key of the block) -> BlockHandle (offset, size), restart interval 1
+    i0 = entry(0, b'ab/x', varint(off0) + varint(len(b0)))
+    i1 = entry(0, b'cd/b', varint(off1) + varint(len(b1)))
+    index = i0 + i1 + (0).to_bytes(4, 'little') + len(i0).to_bytes(4, 'little') + (2).to_bytes(4, 'little')
+    footer = varint(off_meta) + varint(len(meta)) + varint(off_index) + varint(len(index))
+    footer += bytes(40 - len(footer)) + bytes([0x57, 0xfb, 0x80, 0x8b, 0x24, 0x75, 0x47, 0xdb])
+    table = b0 + _trailer(b0) + b1 + _trailer(b1) + meta + _trailer(meta) + index + _trailer(index) + footer
+
+    prefix = str(tmp_path / 'hand')
+    open(prefix + '.index', 'wb').write(table)
+    open(prefix + '.data-00000-of-00001', 'wb').write(data)
+    got = ck.read_tf_checkpoint(prefix, verify=True)
+    assert set(got) == {'ab/w', 'cd/b'}
+    assert got['ab/w'].dtype == np.float32 and np.array_equal(got['ab/w'], f32)
+    assert got['cd/b'].dtype == np.int64 and got['cd/b'].shape == (1, 2) and np.array_equal(got['cd/b'], i64)
+
+    # a flipped bit inside a data block must trip the block trailer CRC; one in the tensor bytes the per-tensor CRC
+    bad = bytearray(table)
+    bad[off1 + 3] ^= 0x01
+    open(prefix + '.index', 'wb').write(bytes(bad))
+    with pytest.raises(ValueError, match='checksum'):
+        ck.read_tf_checkpoint(prefix)
+    open(prefix + '.index', 'wb').write(table)
+    bad = bytearray(data)
+    bad[1] ^= 0x10
+    open(prefix + '.data-00000-of-00001', 'wb').write(bytes(bad))
+    with pytest.raises(ValueError, match='checksum'):
+        ck.read_tf_checkpoint(prefix, verify=True)
+
+
+def test_writer_output_matches_hand_assembled_bytes(tmp_path):
+    """The writer, on one small tensor, must produce exactly the bytes the format description gives."""
+    arr = np.array([1.0, 2.0], dtype=np.float32)
+    prefix = str(tmp_path / 'w')
+    ck.write_tf_checkpoint(prefix, {'k': arr})
+    raw = arr.astype('<f4').tobytes()
+    crc = _crc32c_bitwise(raw)
+    masked = (((crc >> 15) | (crc << 17)) + 0xa282ead8) & 0xFFFFFFFF
+    header = bytes([0x08, 0x01, 0x1a, 0x02, 0x08, 0x01])
+    e = bytes([0x08, 0x01, 0x12, 0x04, 0x12, 0x02, 0x08, 0x02, 0x28, 0x08, 0x35]) + masked.to_bytes(4, 'little')
+    b0 = bytes([0, 0, len(header)]) + header + bytes([0, 1, len(e)]) + b'k' + e + (0).to_bytes(4, 'little') + (1).to_bytes(4, 'little')
+    meta = (0).to_bytes(4, 'little') + (1).to_bytes(4, 'little')
+    off_meta = len(b0) + 5
+    off_index = off_meta + len(meta) + 5
+    handle = bytes([0, len(b0)])
+    index = bytes([0, 1, len(handle)]) + b'k' + handle + (0).to_bytes(4, 'little') + (1).to_bytes(4, 'little')
+    footer = bytes([off_meta, len(meta), off_index, len(index)])
+    footer += bytes(40 - len(footer)) + bytes([0x57, 0xfb, 0x80, 0x8b, 0x24, 0x75, 0x47, 0xdb])
+    want = b0 + _trailer(b0) + meta + _trailer(meta) + index + _trailer(index) + footer
+    assert open(prefix + '.index', 'rb').read() == want
+    assert open(prefix + '.data-00000-of-00001', 'rb').read() == raw

@@ -10,7 +10,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libraft_b200.so')
+# RAFT_B200_LIB: load another build of the same sources (kernel experiments, tools/epi_exp.sh); the default is the in-tree build.
+LIB_PATH = os.environ.get('RAFT_B200_LIB') or os.path.join(_HERE, 'libraft_b200.so')
 
 PREC_FP32 = 0
 PREC_F16X2 = 1

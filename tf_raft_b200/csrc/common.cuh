@@ -38,8 +38,13 @@ __host__ __device__ constexpr int round_up(int a, int b) { return ceil_div(a, b)
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
   v = fminf(fmaxf(v, -65504.f), 65504.f);            // saturate instead of inf -> NaN downstream
+#if defined(RAFT_EPI_EXP) && (RAFT_EPI_EXP & 8)
+  hi = __ushort_as_half((unsigned short)(__float_as_uint(v) >> 16));      // experiment: no conversions
+  lo = __ushort_as_half((unsigned short)__float_as_uint(v));
+#else
   hi = __float2half_rn(v);
   lo = __float2half_rn(v - __half2float(hi));
+#endif
 }
 
 __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {

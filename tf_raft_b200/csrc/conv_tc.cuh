@@ -92,12 +92,22 @@ __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<floa
 // 32-byte global store (STG.256, sm_100): the thread-per-row epilogues write a full 32-byte sector per lane and instruction
 // instead of half of one -- half as many store instructions and LSU wavefronts for the same bytes.  `p` must be 32-byte aligned.
 __device__ __forceinline__ void st8u(void* p, const uint32_t (&r)[8]) {
+#if defined(RAFT_EPI_EXP) && (RAFT_EPI_EXP & 1)
+  if (r[0] != 0x7fc12345u) return;          // experiment: no epilogue stores (tools/epi_exp.sh)
+#endif
   asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
                "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
 // 32-byte loads: L2-coherent (tensors another CTA of the same grid may have written) and read-only forms.
 __device__ __forceinline__ void ldcg8(const float* p, float (&r)[8]) {
+#if defined(RAFT_EPI_EXP) && (RAFT_EPI_EXP & 2)
+  if (p != nullptr) {                        // experiment: no epilogue operand loads
+#pragma unroll
+    for (int e = 0; e < 8; ++e) r[e] = 0.5f;
+    return;
+  }
+#endif
   asm volatile("ld.global.cg.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
                : "l"(p));
@@ -116,7 +126,11 @@ __device__ __forceinline__ void st8f(float* p, float a, float b, float c, float 
 // so they must not be served from this SM's L1 nor through the non-coherent path.
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 
+#if defined(RAFT_EPI_EXP) && (RAFT_EPI_EXP & 4)
+__device__ __forceinline__ float fast_sigmoid(float x) { return x; }      // experiment: no MUFU
+#else
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+#endif
 __device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
 
 // ------------------------------------------------------------------------------------------------

@@ -557,7 +557,7 @@ __device__ __forceinline__ void norm_merge_channel(const float* __restrict__ par
 // arrives LAST at the group's counter merges them (same order whichever block that is) and writes
 //   mean[g][c]  and  mult[g][c] = rsqrt(var + eps) * gamma[c]   (the multiplier applied to (y - mean)),
 // then resets the counter for the next launch.  (Round 1 ran the finalisation as a second 7 us launch per norm layer.)
-__global__ void __launch_bounds__(256) norm_stats_kernel(const float* __restrict__ y, int P, int C, int nsplit,
+__global__ void __launch_bounds__(256, 6) norm_stats_kernel(const float* __restrict__ y, int P, int C, int nsplit,
                                                          float* __restrict__ part, const float* __restrict__ gamma, float eps,
                                                          float* __restrict__ mean_out, float* __restrict__ mult_out,
                                                          unsigned int* __restrict__ counter) {

@@ -250,11 +250,13 @@ static int gru_tc(const UpdateCtx& c, float* h, int lzr, int lq, int hid, int x_
 
 // Flow branch of BasicMotionEncoder (update.py:98-99): convf1 7x7 2->128 + relu, convf2 3x3 128->64 + relu ->
 // cor_flo[192:256).  Depends only on the current flow, so it may run beside the lookup and the correlation branch.
-static int flow_branch_basic_tc(const UpdateCtx& c) {
+// (two parts, so that the work list of update_mega_kernel can interleave them with the correlation branch: the list order is
+//  the order in which free CTAs claim items)
+static int flow_branch_basic_tc(const UpdateCtx& c, int part) {
   const Workspace& W = c.W;
   const VariantDims d = variant_dims(c.variant);
   TcConvParams p;
-  {  // convf1 7x7 2->128 + relu: K = 98 -> gather the window into 128-channel planes, run as a 1x1 GEMM
+  if (part == 0) {  // convf1 7x7 2->128 + relu: K = 98 -> gather the window into 128-channel planes, run as a 1x1 GEMM
     const size_t npix = (size_t)c.B * c.h * c.w;
     flow_im2col_kernel<<<grid_for(npix * 128), 256, 0, c.stream>>>(W.flow, c.B, c.h, c.w, W.fim_hi, W.fim_lo);
     RAFT_COUNT_LAUNCH();
@@ -262,8 +264,7 @@ static int flow_branch_basic_tc(const UpdateCtx& c) {
     p.out_hi = W.flo1_hi; p.out_lo = W.flo1_lo; p.h_stride = d.s_flo1;
     TcSeg s[1] = {{W.fim_hi, W.fim_lo, 128, 0, 2}};
     RAFT_TRY(launch_tc_layer(c, 11, 1, s, p));
-  }
-  {  // convf2 3x3 128->64 + relu -> cor_flo[192:256)
+  } else {  // convf2 3x3 128->64 + relu -> cor_flo[192:256)
     tc_params_init(p, EPI_LINEAR, ACT_RELU, 64);
     p.out_hi = W.cf_hi; p.out_lo = W.cf_lo; p.h_stride = d.s_cf; p.h_c0 = 192;
     TcSeg s[1] = {{W.flo1_hi, W.flo1_lo, d.s_flo1, 0, 2}};
@@ -284,13 +285,14 @@ static int update_core_tc(const UpdateCtx& c, float* h, float* delta, float* mas
       TcSeg s[1] = {{W.corr_hi, W.corr_lo, d.s_corr, 0, d.s_corr / kChunkK}};
       RAFT_TRY(launch_tc_layer(c, 0, 1, s, p));
     }
+    RAFT_TRY(flow_branch_basic_tc(c, 0));                   // convf1 (update.py:98)
     {  // convc2 3x3 256->192 + relu -> cor_flo[0:192)
       tc_params_init(p, EPI_LINEAR, ACT_RELU, 192);
       p.out_hi = W.cf_hi; p.out_lo = W.cf_lo; p.h_stride = d.s_cf;
       TcSeg s[1] = {{W.cor1_hi, W.cor1_lo, d.s_cor1, 0, 4}};
       RAFT_TRY(launch_tc_layer(c, 1, 1, s, p, -1, dep1(0)));
     }
-    RAFT_TRY(flow_branch_basic_tc(c));                      // convf1, convf2 (update.py:98-99)
+    RAFT_TRY(flow_branch_basic_tc(c, 1));                   // convf2 (update.py:99)
     {  // conv 3x3 256->126 + relu, concat flow -> x[128:256)
       tc_params_init(p, EPI_LINEAR, ACT_RELU, 126);
       p.out_hi = W.x_hi; p.out_lo = W.x_lo; p.h_stride = d.s_x; p.h_c0 = 128;

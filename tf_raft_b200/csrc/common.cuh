@@ -47,6 +47,23 @@ __device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
 #endif
 }
 
+// Two values at once: the packed conversion (cvt.rn.f16x2.f32 -> F2FP.F16.F32.PACK_AB, ALU pipe) instead of two scalar F2F
+// (conversion pipe, a quarter of the rate).  Same roundings as split_f16; lane order as pack_h2 (a in the low half).
+__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi2, uint32_t& lo2) {
+  a = fminf(fmaxf(a, -65504.f), 65504.f);
+  b = fminf(fmaxf(b, -65504.f), 65504.f);
+#if defined(RAFT_EPI_EXP) && (RAFT_EPI_EXP & 8)
+  hi2 = __float_as_uint(a) ^ (__float_as_uint(b) << 16);
+  lo2 = __float_as_uint(b) ^ (__float_as_uint(a) << 16);
+#else
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi2 = *reinterpret_cast<const uint32_t*>(&h);
+  lo2 = *reinterpret_cast<const uint32_t*>(&l);
+#endif
+}
+
 __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
   return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
 }

@@ -299,13 +299,7 @@ __device__ __forceinline__ void tc_epilogue_regs(const TcConvParams& p, float (&
     for (int q = 0; q < 2; ++q) {
       uint32_t ph[8], pl[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        __half h0, l0, h1, l1;
-        split_f16(v[16 * q + 2 * e], h0, l0);
-        split_f16(v[16 * q + 2 * e + 1], h1, l1);
-        ph[e] = pack_h2(h0, h1);
-        pl[e] = pack_h2(l0, l1);
-      }
+      for (int e = 0; e < 8; ++e) split_f16x2(v[16 * q + 2 * e], v[16 * q + 2 * e + 1], ph[e], pl[e]);
       if (wide) {
         st8u(dhi + 16 * q, ph);
         st8u(dlo + 16 * q, pl);
@@ -327,17 +321,18 @@ __device__ __forceinline__ void tc_epilogue_regs(const TcConvParams& p, float (&
 // pixr[k] is the flat pixel index of row k (-1 = outside the image).
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void store_split4(__half* hi, __half* lo, size_t o, bool aligned, const float (&v)[4]) {
-  __half h[4], l[4];
-#pragma unroll
-  for (int e = 0; e < 4; ++e) split_f16(v[e], h[e], l[e]);
+  uint32_t h01, l01, h23, l23;
+  split_f16x2(v[0], v[1], h01, l01);
+  split_f16x2(v[2], v[3], h23, l23);
   if (aligned) {
-    *reinterpret_cast<uint2*>(hi + o) = make_uint2(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]));
-    *reinterpret_cast<uint2*>(lo + o) = make_uint2(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]));
+    *reinterpret_cast<uint2*>(hi + o) = make_uint2(h01, h23);
+    *reinterpret_cast<uint2*>(lo + o) = make_uint2(l01, l23);
   } else {
+    const uint32_t hh[2] = {h01, h23}, ll[2] = {l01, l23};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      hi[o + e] = h[e];
-      lo[o + e] = l[e];
+      hi[o + e] = __ushort_as_half((unsigned short)(hh[e >> 1] >> (16 * (e & 1))));
+      lo[o + e] = __ushort_as_half((unsigned short)(ll[e >> 1] >> (16 * (e & 1))));
     }
   }
 }

@@ -281,11 +281,10 @@ struct CorrPrepParams {
 };
 
 __device__ __forceinline__ void store_split2(__half* hi, __half* lo, size_t o, float x, float y) {
-  __half h0, l0, h1, l1;
-  split_f16(x, h0, l0);
-  split_f16(y, h1, l1);
-  *reinterpret_cast<uint32_t*>(hi + o) = pack_h2(h0, h1);
-  *reinterpret_cast<uint32_t*>(lo + o) = pack_h2(l0, l1);
+  uint32_t h2, l2;
+  split_f16x2(x, y, h2, l2);
+  *reinterpret_cast<uint32_t*>(hi + o) = h2;
+  *reinterpret_cast<uint32_t*>(lo + o) = l2;
 }
 __device__ __forceinline__ float pool4(float a, float b, float c, float d) {
   return __fmul_rn(__fadd_rn(__fadd_rn(a, b), __fadd_rn(c, d)), 0.25f);
@@ -297,10 +296,11 @@ __global__ void __launch_bounds__(128) corr_prep_kernel(const CorrPrepParams p) 
     const size_t nb = gridDim.x - p.npatch;
     for (size_t i = (size_t)(blockIdx.x - p.npatch) * blockDim.x + threadIdx.x; i < n4; i += nb * blockDim.x) {
       const float4 v = __ldg(reinterpret_cast<const float4*>(p.f1) + i);
-      __half h[4], l[4];
-      split_f16(v.x, h[0], l[0]); split_f16(v.y, h[1], l[1]); split_f16(v.z, h[2], l[2]); split_f16(v.w, h[3], l[3]);
-      reinterpret_cast<uint2*>(p.f1_hi)[i] = make_uint2(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]));
-      reinterpret_cast<uint2*>(p.f1_lo)[i] = make_uint2(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]));
+      uint32_t h01, l01, h23, l23;
+      split_f16x2(v.x, v.y, h01, l01);
+      split_f16x2(v.z, v.w, h23, l23);
+      reinterpret_cast<uint2*>(p.f1_hi)[i] = make_uint2(h01, h23);
+      reinterpret_cast<uint2*>(p.f1_lo)[i] = make_uint2(l01, l23);
     }
     return;
   }

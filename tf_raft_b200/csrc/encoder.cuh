@@ -81,7 +81,6 @@ struct EncWs {
   float *X32, *O32, *Y32, *D32;
   __half *Xh, *Xl, *Oh, *Ol, *Fh, *Fl, *Ih, *Il;
   float *part, *mean, *mult;
-  unsigned int* counter;      // per statistics group: blocks of norm_stats_kernel that have delivered their partials
   size_t total;
 };
 constexpr int kNormSplit = 64;
@@ -110,7 +109,6 @@ inline EncWs enc_ws_layout(void* base, int variant, int N, int H, int W) {
     E.Ih = (__half*)take(np1 * 192 * 2); E.Il = (__half*)take(np1 * 192 * 2);
   }
   E.part = (float*)take((size_t)N * kNormSplit * 3 * 256 * 4);
-  E.counter = (unsigned int*)take((size_t)N * sizeof(unsigned int));
   E.mean = (float*)take((size_t)N * 256 * 4);
   E.mult = (float*)take((size_t)N * 256 * 4);
   E.total = off;
@@ -202,11 +200,13 @@ inline int enc_norm_apply(const EncCtx& c, const EncNormSlot& ns, const float* y
   const int Pg = c.per_image ? P : (int)npix;
   const float* gamma = reinterpret_cast<const float*>(c.prep + ns.gamma);
   const float* beta = reinterpret_cast<const float*>(c.prep + ns.beta);
-  norm_stats_kernel<<<dim3((unsigned)G, kNormSplit), 256, 0, c.st>>>(y, Pg, C, kNormSplit, c.W.part, gamma, 1e-3f, c.W.mean,
-                                                                     c.W.mult, c.W.counter);
+  // (Finalisation inside norm_stats_kernel by the last block of a group was measured twice -- +33 us per launch: the merge
+  //  of C channels by one block is serial where norm_final_kernel spreads it over G*C warps; profiles/README.md.)
+  norm_stats_kernel<<<dim3((unsigned)G, kNormSplit), 256, 0, c.st>>>(y, Pg, C, kNormSplit, c.W.part);
+  norm_final_kernel<<<ceil_div(G * C * 32, 256), 256, 0, c.st>>>(c.W.part, G, C, kNormSplit, gamma, 1e-3f, c.W.mean, c.W.mult);
   norm_apply_kernel<<<grid_for(npix * (pad64(C) / 8)), 256, 0, c.st>>>(y, npix, P, C, c.per_image, c.W.mean, c.W.mult, beta, relu,
                                                                  skip32, skip_hi, skip_lo, out32, hi, lo, pad64(C));
-  g_launches += 2;
+  g_launches += 3;
   return raft_launch_status();
 }
 
@@ -296,7 +296,6 @@ inline int encoder_forward(int variant, int norm_type, int out_dim, const void* 
   const EncSpec S = enc_spec(variant);
   const EncLayout& L = c.L;
   const EncWs& E = c.W;
-  if (c.stats) RAFT_CUDA_TRY(cudaMemsetAsync(E.counter, 0, (size_t)N * sizeof(unsigned int), st));   // (the workspace is uninitialised)
 
   // ---- stem: conv1 7x7 s2 + norm1 + relu (extractor.py:120) ----
   // K = 7*7*3 = 147: gather the (normalised) input window of every output pixel into 192-channel fp16 planes

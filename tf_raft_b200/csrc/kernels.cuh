@@ -534,35 +534,9 @@ __device__ __forceinline__ void chan_merge(float& na, float& ma, float& m2a, flo
   m2a = m2a + m2b + d * d * (na * nb / n);
   na = n;
 }
-// Merge of the nsplit partial triples of channel (g, c) by ONE warp: lanes merge their partials, then a fixed xor-shuffle
-// tree (deterministic; both partners of a shuffle compute the same merged triple, in lane order).
-__device__ __forceinline__ void norm_merge_channel(const float* __restrict__ part, int g, int c, int C, int nsplit, int lane,
-                                                   float& n, float& mean, float& m2) {
-  n = 0.f; mean = 0.f; m2 = 0.f;
-  for (int s = lane; s < nsplit; s += 32) {
-    const float* o = part + (((size_t)g * nsplit + s) * 3) * C + c;
-    chan_merge(n, mean, m2, __ldcg(o), __ldcg(o + C), __ldcg(o + 2 * C));     // written by other blocks of this grid: L2
-  }
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    const float nb = __shfl_xor_sync(0xffffffffu, n, off), mb = __shfl_xor_sync(0xffffffffu, mean, off),
-                m2b = __shfl_xor_sync(0xffffffffu, m2, off);
-    float na = n, ma = mean, m2a = m2;
-    if (lane & off) { na = nb; ma = mb; m2a = m2b; chan_merge(na, ma, m2a, n, mean, m2); }
-    else chan_merge(na, ma, m2a, nb, mb, m2b);
-    n = na; mean = ma; m2 = m2a;
-  }
-}
-// Statistics pass + finalisation in one launch: grid (G, nsplit); every block writes its partial triples, the block that
-// arrives LAST at the group's counter merges them (same order whichever block that is) and writes
-//   mean[g][c]  and  mult[g][c] = rsqrt(var + eps) * gamma[c]   (the multiplier applied to (y - mean)),
-// then resets the counter for the next launch.  (Round 1 ran the finalisation as a second 7 us launch per norm layer.)
-__global__ void __launch_bounds__(256, 6) norm_stats_kernel(const float* __restrict__ y, int P, int C, int nsplit,
-                                                         float* __restrict__ part, const float* __restrict__ gamma, float eps,
-                                                         float* __restrict__ mean_out, float* __restrict__ mult_out,
-                                                         unsigned int* __restrict__ counter) {
+__global__ void __launch_bounds__(256) norm_stats_kernel(const float* __restrict__ y, int P, int C, int nsplit,
+                                                         float* __restrict__ part) {
   __shared__ float red[3][256];
-  __shared__ int is_last;
   const int g = blockIdx.x, sp = blockIdx.y;
   const int lanes = 256 / C > 0 ? 256 / C : 1;          // pixel lanes per block (C <= 256)
   const int c = threadIdx.x % C, pl = threadIdx.x / C;
@@ -589,25 +563,33 @@ __global__ void __launch_bounds__(256, 6) norm_stats_kernel(const float* __restr
     float* o = part + (((size_t)g * nsplit + sp) * 3) * C + c;
     o[0] = n; o[C] = mean; o[2 * C] = m2;
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    // One gpu-scope fence per block (cumulative over the block's partials through the barrier above) -- a fence in every
-    // thread cost +52 us per launch (profiles/r02_launches_trip11.txt).
-    __threadfence();
-    is_last = atomicAdd(&counter[g], 1u) == (unsigned)(nsplit - 1);
-    __threadfence();
+}
+// mean[g][c] and mult[g][c] = rsqrt(var + eps) * gamma[c]  (the multiplier applied to (y - mean)).
+// One warp per (g, c): lanes merge their partials, then a fixed xor-shuffle tree (deterministic).
+__global__ void norm_final_kernel(const float* __restrict__ part, int G, int C, int nsplit,
+                                  const float* __restrict__ gamma, float eps, float* __restrict__ mean_out,
+                                  float* __restrict__ mult_out) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (i >= G * C) return;
+  const int g = i / C, c = i % C;
+  float n = 0.f, mean = 0.f, m2 = 0.f;
+  for (int s = lane; s < nsplit; s += 32) {
+    const float* o = part + (((size_t)g * nsplit + s) * 3) * C + c;
+    chan_merge(n, mean, m2, o[0], o[C], o[2 * C]);
   }
-  __syncthreads();
-  if (is_last) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int cc = warp; cc < C; cc += 8) {
-      norm_merge_channel(part, g, cc, C, nsplit, lane, n, mean, m2);
-      if (lane == 0) {
-        mean_out[g * C + cc] = mean;
-        mult_out[g * C + cc] = rsqrtf(m2 / n + eps) * gamma[cc];
-      }
-    }
-    if (threadIdx.x == 0) counter[g] = 0u;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const float nb = __shfl_xor_sync(0xffffffffu, n, off), mb = __shfl_xor_sync(0xffffffffu, mean, off),
+                m2b = __shfl_xor_sync(0xffffffffu, m2, off);
+    // both partners compute the same merged triple (merge in lane order so the result is bitwise identical)
+    float na = n, ma = mean, m2a = m2;
+    if (lane & off) { na = nb; ma = mb; m2a = m2b; chan_merge(na, ma, m2a, n, mean, m2); }
+    else chan_merge(na, ma, m2a, nb, mb, m2b);
+    n = na; mean = ma; m2 = m2a;
+  }
+  if (lane == 0) {
+    mean_out[i] = mean;
+    mult_out[i] = rsqrtf(m2 / n + eps) * gamma[c];
   }
 }
 // out = [relu]((y - mean) * a + beta);  optional skip: out = relu(skip + out)  (ResBlock, extractor.py:41-49)
@@ -663,13 +645,7 @@ __global__ void norm_apply_kernel(const float* __restrict__ y, size_t npix, int 
     if (hi) {
       uint32_t ph[4], pl[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        __half h0, l0, h1, l1;
-        split_f16(v[2 * e], h0, l0);
-        split_f16(v[2 * e + 1], h1, l1);
-        ph[e] = pack_h2(h0, h1);
-        pl[e] = pack_h2(l0, l1);
-      }
+      for (int e = 0; e < 4; ++e) split_f16x2(v[2 * e], v[2 * e + 1], ph[e], pl[e]);
       *reinterpret_cast<uint4*>(hi + px * c_pad + c) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
       *reinterpret_cast<uint4*>(lo + px * c_pad + c) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
     }
@@ -712,13 +688,7 @@ __global__ void stem_im2col_kernel(const float* __restrict__ img, int N, int H, 
         if (++j == 21) { j = 0; ++ty; }
       }
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        __half h0, l0, h1, l1;
-        split_f16(v[2 * e], h0, l0);
-        split_f16(v[2 * e + 1], h1, l1);
-        ph[e] = pack_h2(h0, h1);
-        pl[e] = pack_h2(l0, l1);
-      }
+      for (int e = 0; e < 4; ++e) split_f16x2(v[2 * e], v[2 * e + 1], ph[e], pl[e]);
     }
     reinterpret_cast<uint4*>(hi)[i] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
     reinterpret_cast<uint4*>(lo)[i] = make_uint4(pl[0], pl[1], pl[2], pl[3]);

@@ -41,7 +41,9 @@ struct alignas(64) MegaParams {
   MegaLayer layer[kMegaMaxLayers];
   int nlayers, nitems;
   unsigned int* flags;            // zeroed before the launch
+  unsigned int* next_item;        // work-list cursor (zeroed with the flags): CTAs claim items with atomicAdd
 };
+constexpr int kMegaQueue = 16;    // per-CTA ring of claimed item numbers (producer -> issuer / epilogue warps)
 
 #if defined(__CUDA_ARCH__)
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
@@ -80,7 +82,9 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
   uint64_t* empty_bar = full_bar + kMegaMaxStages;
   uint64_t* acc_full = empty_bar + kMegaMaxStages;      // [2] issuer -> promotion warps
   uint64_t* acc_empty = acc_full + 2;                   // [2] promotion warps -> issuer
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* q_bar = acc_empty + 2;                      // [kMegaQueue] producer -> consumers: item number published
+  int* item_q = reinterpret_cast<int*>(q_bar + kMegaQueue);
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(item_q + kMegaQueue);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -94,6 +98,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], kMegaEpiWarps);          // every epilogue warp arrives, with or without columns
     }
+    for (int i = 0; i < kMegaQueue; ++i) mbar_init(&q_bar[i], 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -110,7 +115,16 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
     if (elect_one()) {
       uint32_t par = 0, used = 0;          // per ring slot: parity of its use count, used since the last drain
       int slot = 0, cur_nst = 0, cur_bytes = 0;
-      for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
+      // Items are CLAIMED, not pre-assigned: a CTA that becomes free takes the lowest unclaimed item of the list (layer
+      // order = priority order), so no CTA sits on a blocked item while a runnable one waits behind it in a fixed
+      // per-CTA sequence.  Every dependency points to a lower item number, which some co-resident CTA has already claimed,
+      // so the wait graph stays acyclic.  The claimed number is handed to the other roles through item_q / q_bar.
+      int item = (int)atomicAdd(P.next_item, 1u);
+      for (int k = 0;; ++k) {
+        item_q[k & (kMegaQueue - 1)] = item < P.nitems ? item : -1;
+        mbar_arrive(&q_bar[k & (kMegaQueue - 1)]);       // (release: the slot's item number is visible to the waiters)
+        if (item >= P.nitems) break;
+        int nxt = P.nitems;
         int L, nt, b, ty, tx;
         mega_decode(P, item, L, nt, b, ty, tx);
         const MegaLayer& ML = P.layer[L];
@@ -148,11 +162,15 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
         }
         const int ntaps = c.kh * c.kw;
         const int x0 = tx * c.TW * c.stride, y0 = ty * c.TH * c.stride, n0 = nt * c.bn;
+        int left = ntaps * (c.seg_chunks[0] + (c.nseg > 1 ? c.seg_chunks[1] : 0));
         for (int tap = 0; tap < ntaps; ++tap) {
           const int dy = tap / c.kw - c.ph, dx = tap % c.kw - c.pw;
           int kc = 0;
           for (int seg = 0; seg < c.nseg; ++seg) {
             for (int ch = 0; ch < c.seg_chunks[seg]; ++ch, ++kc) {
+              // claim the next item while the last stage of this one is still to be loaded: late enough that the CTA is
+              // about to be free, early enough that the atomic's round trip hides behind the slot wait below
+              if (--left == 0) nxt = (int)atomicAdd(P.next_item, 1u);
               const int s = slot;
               slot = slot + 1 == cur_nst ? 0 : slot + 1;
               mbar_wait(&empty_bar[s], ((par >> s) & 1u) ^ 1u);
@@ -165,13 +183,17 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
             }
           }
         }
+        item = nxt;
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     uint32_t par = 0;
     int slot = 0, cur_nst = 0, cur_bytes = 0, gg = 0;
-    for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
+    for (int k = 0;; ++k) {
+      mbar_wait(&q_bar[k & (kMegaQueue - 1)], (uint32_t)(k / kMegaQueue) & 1u);
+      const int item = item_q[k & (kMegaQueue - 1)];
+      if (item < 0) break;
       int L, nt, b, ty, tx;
       mega_decode(P, item, L, nt, b, ty, tx);
       const TcConvParams& c = P.layer[L].c;
@@ -224,7 +246,10 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
     const int m = quarter * 32 + lane;               // tile row == TMEM lane
     const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
     int gg = 0;
-    for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
+    for (int k = 0;; ++k) {
+      mbar_wait(&q_bar[k & (kMegaQueue - 1)], (uint32_t)(k / kMegaQueue) & 1u);
+      const int item = item_q[k & (kMegaQueue - 1)];
+      if (item < 0) break;
       int L = 0;
       while (L + 1 < P.nlayers && item >= P.layer[L + 1].item0) ++L;
       const MegaLayer& ML = P.layer[L];
@@ -362,7 +387,7 @@ struct MegaPlan {
   }
 };
 
-inline int mega_flag_words(int B, int tiles) { return kMegaMaxLayers * 3 * B * tiles; }   // upper bound used by the workspace layout
+inline int mega_flag_words(int B, int tiles) { return kMegaMaxLayers * 3 * B * tiles + 1; }   // upper bound used by the workspace layout
 
 // Appends a planned layer (p complete except for the launch fields).  Mirrors the checks of tc_launch().
 inline int mega_add(MegaPlan& M, int layer_id, TcConvParams& p, int n_tiles_n, const TcDeps& deps) {
@@ -403,8 +428,9 @@ inline int mega_add(MegaPlan& M, int layer_id, TcConvParams& p, int n_tiles_n, c
 
 inline int mega_launch(MegaPlan& M, unsigned int* flags, size_t flag_words, bool zero_flags, cudaStream_t stream) {
   if (M.P.nlayers == 0) return RAFT_OK;
-  if ((size_t)M.nflags > flag_words) return RAFT_ERR_WORKSPACE;
+  if ((size_t)M.nflags + 1 > flag_words) return RAFT_ERR_WORKSPACE;
   M.P.flags = flags;
+  M.P.next_item = flags + M.nflags;
   int dev = 0;
   RAFT_CUDA_TRY(cudaGetDevice(&dev));
   static unsigned long long attr_mask = 0;          // per-device attribute (benign race: idempotent)
@@ -412,7 +438,7 @@ inline int mega_launch(MegaPlan& M, unsigned int* flags, size_t flag_words, bool
     RAFT_CUDA_TRY(cudaFuncSetAttribute(update_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_mask |= 1ull << (dev & 63);
   }
-  if (zero_flags) RAFT_CUDA_TRY(cudaMemsetAsync(flags, 0, (size_t)M.nflags * sizeof(unsigned int), stream));
+  if (zero_flags) RAFT_CUDA_TRY(cudaMemsetAsync(flags, 0, ((size_t)M.nflags + 1) * sizeof(unsigned int), stream));
   // All CTAs must be co-resident (items wait on items of other CTAs): one CTA per SM, never more CTAs than SMs.
   static int num_sms[64] = {0};
   if (!num_sms[dev & 63]) RAFT_CUDA_TRY(cudaDeviceGetAttribute(&num_sms[dev & 63], cudaDevAttrMultiProcessorCount, dev));

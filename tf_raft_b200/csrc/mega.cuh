@@ -51,12 +51,6 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void red_release_gpu_add(unsigned int* p, unsigned int v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -135,6 +129,28 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
         mega_decode(P, item, L, nt, b, ty, tx);
         const MegaLayer& ML = P.layer[L];
         const TcConvParams& c = ML.c;
+        // ---- dependencies: tiles of the source layers that cover this tile's halo ----
+        if (ML.ndep > 0) {
+          const int mtiles = c.B * c.tiles_y * c.tiles_x;
+          for (int d = 0; d < ML.ndep; ++d) {
+            const MegaLayer& SL = P.layer[ML.dep_layer[d]];
+            const int n_lo = ML.dep_ntile[d] < 0 ? 0 : ML.dep_ntile[d];
+            const int n_hi = ML.dep_ntile[d] < 0 ? SL.c.n_tiles_n - 1 : ML.dep_ntile[d];
+            for (int n = n_lo; n <= n_hi; ++n)
+              for (int yy = max(0, ty - ML.dep_ry); yy <= min(c.tiles_y - 1, ty + ML.dep_ry); ++yy)
+                for (int xx = max(0, tx - ML.dep_rx); xx <= min(c.tiles_x - 1, tx + ML.dep_rx); ++xx) {
+                  const unsigned int* f = P.flags + SL.flag0 + n * mtiles + (b * c.tiles_y + yy) * c.tiles_x + xx;
+                  if (ld_acquire_gpu(f) < (unsigned)kMegaEpiWarps) {
+                    const long long t0 = clock64();
+                    while (ld_acquire_gpu(f) < (unsigned)kMegaEpiWarps) {
+                      __nanosleep(64);
+                      if (clock64() - t0 > 8000000000LL) __trap();        // protocol bug -> trapped kernel, never a hang
+                    }
+                  }
+                }
+          }
+          fence_proxy_async_all();          // acquired generic-proxy writes -> visible to the TMA loads issued below
+        }
         // ---- ring geometry: a layer with another stage size re-carves the ring once it has drained ----
         if (c.nstages != cur_nst || c.stage_bytes != cur_bytes) {
           for (int s = 0; s < kMegaMaxStages; ++s)
@@ -146,110 +162,26 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
         }
         const int ntaps = c.kh * c.kw;
         const int x0 = tx * c.TW * c.stride, y0 = ty * c.TH * c.stride, n0 = nt * c.bn;
-        const int per_tap = c.seg_chunks[0] + (c.nseg > 1 ? c.seg_chunks[1] : 0);
-        const int total = ntaps * per_tap;
-        // stage i of the item = (tap, K chunk kc): activations of segment seg, chunk ch, shifted by the tap; weights (kc, tap)
-        auto load_a = [&](int i, int s) {
-          const int tap = i / per_tap, kc = i - tap * per_tap;
-          const int seg = kc < c.seg_chunks[0] ? 0 : 1, ch = seg ? kc - c.seg_chunks[0] : kc;
+        int left = ntaps * (c.seg_chunks[0] + (c.nseg > 1 ? c.seg_chunks[1] : 0));
+        for (int tap = 0; tap < ntaps; ++tap) {
           const int dy = tap / c.kw - c.ph, dx = tap % c.kw - c.pw;
-          tma_load_5d(stages + (size_t)s * cur_bytes, &c.a_map[seg], &full_bar[s], c.seg_c0[seg] + ch * kChunkK, x0 + dx, y0 + dy, b, 0);
-        };
-        auto load_b = [&](int i, int s) {
-          const int tap = i / per_tap, kc = i - tap * per_tap;
-          tma_load_4d(stages + (size_t)s * cur_bytes + 2 * kABytes, &c.b_map, &full_bar[s], kc * kChunkK, n0, tap, 0);
-        };
-        auto take_slot = [&]() {
-          const int s = slot;
-          slot = slot + 1 == cur_nst ? 0 : slot + 1;
-          mbar_wait(&empty_bar[s], ((par >> s) & 1u) ^ 1u);
-          par ^= 1u << s;
-          used |= 1u << s;
-          mbar_arrive_expect_tx(&full_bar[s], (uint32_t)cur_bytes);
-          return s;
-        };
-        // The WEIGHTS of the first ring-full of stages do not depend on the source layers: they are requested before the
-        // dependency wait, so that after it only the activation boxes (a third of the bytes) stand between the item and
-        // its first MMA.
-        const int npre = ML.ndep > 0 ? min(cur_nst, total) : 0;
-        int pre[kMegaMaxStages];
-#pragma unroll
-        for (int i = 0; i < kMegaMaxStages; ++i)
-          if (i < npre) {
-            pre[i] = take_slot();
-            load_b(i, pre[i]);
-          }
-        // ---- dependencies: tiles of the source layers that cover this tile's halo ----
-        if (ML.ndep > 0) {
-          const int mtiles = c.B * c.tiles_y * c.tiles_x;
-          for (int d = 0; d < ML.ndep; ++d) {
-            const MegaLayer& SL = P.layer[ML.dep_layer[d]];
-            const int n_lo = ML.dep_ntile[d] < 0 ? 0 : ML.dep_ntile[d];
-            const int n_hi = ML.dep_ntile[d] < 0 ? SL.c.n_tiles_n - 1 : ML.dep_ntile[d];
-            for (int n = n_lo; n <= n_hi; ++n) {
-              const unsigned int* fb = P.flags + SL.flag0 + n * mtiles + b * c.tiles_y * c.tiles_x;
-              if (ML.dep_ry == 1 && ML.dep_rx == 1) {
-                // 3 x 3 neighbourhood: the nine counters are read with independent relaxed loads, all in flight together
-                // (nine dependent acquire loads cost ~6 k cycles per layer boundary); one acquire fence below orders them.
-                long long t0 = 0;
-                for (;;) {
-                  const unsigned int* f[9];
-#pragma unroll
-                  for (int j = 0; j < 9; ++j) {        // neighbours outside the image -> the centre tile (read twice)
-                    const int yy = min(max(ty + j / 3 - 1, 0), c.tiles_y - 1), xx = min(max(tx + j % 3 - 1, 0), c.tiles_x - 1);
-                    f[j] = fb + yy * c.tiles_x + xx;
-                  }
-                  unsigned int v0, v1, v2, v3, v4, v5, v6, v7, v8;
-                  asm volatile(
-                      "ld.relaxed.gpu.global.u32 %0, [%9];\n\t"
-                      "ld.relaxed.gpu.global.u32 %1, [%10];\n\t"
-                      "ld.relaxed.gpu.global.u32 %2, [%11];\n\t"
-                      "ld.relaxed.gpu.global.u32 %3, [%12];\n\t"
-                      "ld.relaxed.gpu.global.u32 %4, [%13];\n\t"
-                      "ld.relaxed.gpu.global.u32 %5, [%14];\n\t"
-                      "ld.relaxed.gpu.global.u32 %6, [%15];\n\t"
-                      "ld.relaxed.gpu.global.u32 %7, [%16];\n\t"
-                      "ld.relaxed.gpu.global.u32 %8, [%17];"
-                      : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3), "=r"(v4), "=r"(v5), "=r"(v6), "=r"(v7), "=r"(v8)
-                      : "l"(f[0]), "l"(f[1]), "l"(f[2]), "l"(f[3]), "l"(f[4]), "l"(f[5]), "l"(f[6]), "l"(f[7]), "l"(f[8])
-                      : "memory");
-                  const unsigned int vmin = min(min(min(v0, v1), min(v2, v3)), min(min(v4, v5), min(min(v6, v7), v8)));
-                  if (vmin >= (unsigned)kMegaEpiWarps) break;
-                  if (t0 == 0) t0 = clock64();
-                  __nanosleep(32);
-                  if (clock64() - t0 > 8000000000LL) __trap();            // protocol bug -> trapped kernel, never a hang
-                }
-              } else {
-                for (int yy = max(0, ty - ML.dep_ry); yy <= min(c.tiles_y - 1, ty + ML.dep_ry); ++yy)
-                  for (int xx = max(0, tx - ML.dep_rx); xx <= min(c.tiles_x - 1, tx + ML.dep_rx); ++xx) {
-                    const unsigned int* f = fb + yy * c.tiles_x + xx;
-                    if (ld_relaxed_gpu(f) < (unsigned)kMegaEpiWarps) {
-                      const long long t0 = clock64();
-                      while (ld_relaxed_gpu(f) < (unsigned)kMegaEpiWarps) {
-                        __nanosleep(64);
-                        if (clock64() - t0 > 8000000000LL) __trap();
-                      }
-                    }
-                  }
-              }
+          int kc = 0;
+          for (int seg = 0; seg < c.nseg; ++seg) {
+            for (int ch = 0; ch < c.seg_chunks[seg]; ++ch, ++kc) {
+              // claim the next item while the last stage of this one is still to be loaded: late enough that the CTA is
+              // about to be free, early enough that the atomic's round trip hides behind the slot wait below
+              if (--left == 0) nxt = (int)atomicAdd(P.next_item, 1u);
+              const int s = slot;
+              slot = slot + 1 == cur_nst ? 0 : slot + 1;
+              mbar_wait(&empty_bar[s], ((par >> s) & 1u) ^ 1u);
+              par ^= 1u << s;
+              used |= 1u << s;
+              uint8_t* st = stages + (size_t)s * cur_bytes;
+              mbar_arrive_expect_tx(&full_bar[s], (uint32_t)cur_bytes);
+              tma_load_5d(st, &c.a_map[seg], &full_bar[s], c.seg_c0[seg] + ch * kChunkK, x0 + dx, y0 + dy, b, 0);
+              tma_load_4d(st + 2 * kABytes, &c.b_map, &full_bar[s], kc * kChunkK, n0, tap, 0);
             }
           }
-          fence_acq_rel_gpu();              // relaxed counter reads + this fence = acquire of the producers' releases
-          fence_proxy_async_all();          // acquired generic-proxy writes -> visible to the TMA loads issued below
-        }
-#pragma unroll
-        for (int i = 0; i < kMegaMaxStages; ++i)
-          if (i < npre) {
-            // (the next item is claimed while the last stage of this one is still to be loaded: late enough that the CTA
-            //  is about to be free, early enough that the atomic's round trip hides behind the slot wait)
-            if (i == total - 1) nxt = (int)atomicAdd(P.next_item, 1u);
-            load_a(i, pre[i]);
-          }
-        for (int i = npre; i < total; ++i) {
-          if (i == total - 1) nxt = (int)atomicAdd(P.next_item, 1u);
-          const int s = take_slot();
-          load_a(i, s);
-          load_b(i, s);
         }
         item = nxt;
       }

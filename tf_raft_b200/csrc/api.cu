@@ -412,9 +412,20 @@ static bool mega_enabled() {
   static const int v = [] { const char* e = getenv("RAFT_B200_MEGA"); return e ? atoi(e) : 1; }();
   return v != 0;
 }
+// CTA pairs (update_mega_kernel<true>) whenever the number of pixel tiles is even; RAFT_B200_PAIR=0 keeps single CTAs (A/B).
+static bool pair_enabled() {
+  static const int v = [] { const char* e = getenv("RAFT_B200_PAIR"); return e ? atoi(e) : 1; }();
+  return v != 0;
+}
 static int update_block_tc(UpdateCtx& c, float* h, float* delta, float* mask, float* adv_coords) {
   MegaPlan plan;
   c.plan = mega_enabled() ? &plan : nullptr;
+  {
+    int tw, th;
+    tc_pick_tile(c.w, c.h, &tw, &th);
+    const int mtiles = c.B * ceil_div(c.h, th) * ceil_div(c.w, tw);
+    plan.pair = pair_enabled() && (mtiles % 2 == 0) ? 1 : 0;
+  }
   const int st = update_core_tc(c, h, delta, mask, adv_coords);
   c.plan = nullptr;
   RAFT_TRY(st);

@@ -82,6 +82,9 @@ struct alignas(64) TcConvParams {
   // flow = coords1 - coords0 (model.py:102, :97) are applied by the thread that holds the pixel's two output columns.
   float* adv_coords;                       // (px, 2) coords1, updated in place; null = no fused advance
   float* adv_flow;                         // (px, 2) coords1 - pixel grid
+  // update_mega_kernel<true> only: the tile is one half of a CTA pair's M = 256 MMA; a stage holds this CTA's 128 activation
+  // rows and HALF of the bn weight rows (b_map's box is bn / 2 rows).
+  int pair;
 };
 
 #if defined(__CUDA_ARCH__)
@@ -714,7 +717,7 @@ inline void tc_pick_tile(int W, int H, int* tw, int* th) {
 inline int tc_finalize(TcConvParams& p) {
   p.tiles_x = ceil_div(p.W, p.TW);
   p.tiles_y = ceil_div(p.H, p.TH);
-  p.stage_bytes = 2 * kABytes + 2 * p.bn * kChunkK * 2;
+  p.stage_bytes = 2 * kABytes + 2 * (p.pair ? p.bn / 2 : p.bn) * kChunkK * 2;
   if (p.row3) p.stage_bytes = kARow3Bytes + 3 * 2 * p.bn * kChunkK * 2;
   const int patch = tc_uses_patch(p.mode) ? kEpiPatchBytes : 0;   // 16 x 2 KB patches (GRU q)
   int nst = (kSmemBudget - patch) / p.stage_bytes;

@@ -56,14 +56,22 @@ __device__ __forceinline__ void red_release_gpu_add(unsigned int* p, unsigned in
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-__device__ __forceinline__ void mega_decode(const MegaParams& P, int item, int& L, int& nt, int& b, int& ty, int& tx) {
+template <bool kPair>
+__device__ __forceinline__ void mega_wait_q(uint64_t* bar, uint32_t parity) {     // item-number queue: filled by the leader CTA
+  if constexpr (kPair) mbar_wait_cluster(bar, parity); else mbar_wait(bar, parity);
+}
+// pair > 0: the item is a PAIR of consecutive pixel tiles (2j, 2j + 1) of one column tile; `rank` picks this CTA's half.
+__device__ __forceinline__ void mega_decode(const MegaParams& P, int item, int& L, int& nt, int& b, int& ty, int& tx, int pair = 0,
+                                            int rank = 0) {
   L = 0;
   while (L + 1 < P.nlayers && item >= P.layer[L + 1].item0) ++L;
   const TcConvParams& c = P.layer[L].c;
   const int mtiles = c.B * c.tiles_y * c.tiles_x;
+  const int units = pair ? mtiles >> 1 : mtiles;
   const int r = item - P.layer[L].item0;
-  nt = r / mtiles;
-  int mt = r - nt * mtiles;
+  nt = r / units;
+  int mt = r - nt * units;
+  if (pair) mt = 2 * mt + rank;
   tx = mt % c.tiles_x;
   mt /= c.tiles_x;
   ty = mt % c.tiles_y;
@@ -71,6 +79,12 @@ __device__ __forceinline__ void mega_decode(const MegaParams& P, int item, int& 
 }
 #endif
 
+// kPair: launched in clusters of two CTAs; an item is a pair of pixel tiles computed by ONE M = 256 MMA stream
+// (tcgen05 cta_group::2) issued by the leader CTA.  Each CTA stages its own activation rows and half of the weight rows, so
+// the weights -- two thirds of the operand bytes of the 256-column layers -- cross the L2 -> SM fabric once per pair instead
+// of once per tile.  Everything downstream of the accumulators (promotion, epilogue, completion counters) is per CTA and
+// identical in both forms; so are the sums (same K order per accumulator).
+template <bool kPair>
 __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __grid_constant__ MegaParams P) {
 #if defined(__CUDA_ARCH__)
   extern __shared__ uint8_t smem_raw[];
@@ -88,6 +102,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int rank = kPair ? (int)cluster_ctarank() : 0;       // 0 = leader: claims the items and issues the MMAs
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kMegaMaxStages; ++s) {
@@ -96,17 +111,22 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], kMegaEpiWarps);          // every epilogue warp arrives, with or without columns
+      mbar_init(&acc_empty[i], kMegaEpiWarps * (kPair ? 2 : 1));   // every epilogue warp (of both CTAs) arrives
     }
     for (int i = 0; i < kMegaQueue; ++i) mbar_init(&q_bar[i], 1);
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_holder, 512u);
-    tmem_relinquish();
+    if constexpr (kPair) {
+      tmem2_alloc(tmem_holder, 512u);
+      tmem2_relinquish();
+    } else {
+      tmem_alloc(tmem_holder, 512u);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kPair) cluster_sync_all(); else __syncthreads();   // (pair: the peer's barriers exist before anything targets them)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
@@ -119,14 +139,26 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
       // order = priority order), so no CTA sits on a blocked item while a runnable one waits behind it in a fixed
       // per-CTA sequence.  Every dependency points to a lower item number, which some co-resident CTA has already claimed,
       // so the wait graph stays acyclic.  The claimed number is handed to the other roles through item_q / q_bar.
-      int item = (int)atomicAdd(P.next_item, 1u);
+      int item = rank == 0 ? (int)atomicAdd(P.next_item, 1u) : 0;
       for (int k = 0;; ++k) {
-        item_q[k & (kMegaQueue - 1)] = item < P.nitems ? item : -1;
-        mbar_arrive(&q_bar[k & (kMegaQueue - 1)]);       // (release: the slot's item number is visible to the waiters)
+        const int qs = k & (kMegaQueue - 1);
+        if (rank == 0) {
+          const int pub = item < P.nitems ? item : -1;
+          item_q[qs] = pub;
+          mbar_arrive(&q_bar[qs]);                       // (release: the slot's item number is visible to the waiters)
+          if constexpr (kPair) {                         // ... and to the three roles of the peer CTA
+            st_cluster_u32(mapa_u32(smem_u32(&item_q[qs]), 1), (uint32_t)pub);
+            mbar_arrive_cluster(mapa_u32(smem_u32(&q_bar[qs]), 1));
+          }
+        } else {
+          mega_wait_q<kPair>(&q_bar[qs], (uint32_t)(k / kMegaQueue) & 1u);
+          item = item_q[qs];
+          if (item < 0) item = P.nitems;
+        }
         if (item >= P.nitems) break;
         int nxt = P.nitems;
         int L, nt, b, ty, tx;
-        mega_decode(P, item, L, nt, b, ty, tx);
+        mega_decode(P, item, L, nt, b, ty, tx, kPair, rank);
         const MegaLayer& ML = P.layer[L];
         const TcConvParams& c = ML.c;
         // ---- dependencies: tiles of the source layers that cover this tile's halo ----
@@ -170,16 +202,24 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
             for (int ch = 0; ch < c.seg_chunks[seg]; ++ch, ++kc) {
               // claim the next item while the last stage of this one is still to be loaded: late enough that the CTA is
               // about to be free, early enough that the atomic's round trip hides behind the slot wait below
-              if (--left == 0) nxt = (int)atomicAdd(P.next_item, 1u);
+              if (--left == 0 && rank == 0) nxt = (int)atomicAdd(P.next_item, 1u);
               const int s = slot;
               slot = slot + 1 == cur_nst ? 0 : slot + 1;
               mbar_wait(&empty_bar[s], ((par >> s) & 1u) ^ 1u);
               par ^= 1u << s;
               used |= 1u << s;
               uint8_t* st = stages + (size_t)s * cur_bytes;
-              mbar_arrive_expect_tx(&full_bar[s], (uint32_t)cur_bytes);
-              tma_load_5d(st, &c.a_map[seg], &full_bar[s], c.seg_c0[seg] + ch * kChunkK, x0 + dx, y0 + dy, b, 0);
-              tma_load_4d(st + 2 * kABytes, &c.b_map, &full_bar[s], kc * kChunkK, n0, tap, 0);
+              if constexpr (kPair) {
+                // both CTAs' boxes complete on the LEADER's barrier, which expects the bytes of both stages
+                if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(2 * cur_bytes));
+                const uint32_t lead = mapa_u32(smem_u32(&full_bar[s]), 0);
+                tma2_load_5d(st, &c.a_map[seg], lead, c.seg_c0[seg] + ch * kChunkK, x0 + dx, y0 + dy, b, 0);
+                tma2_load_4d(st + 2 * kABytes, &c.b_map, lead, kc * kChunkK, n0 + rank * (c.bn >> 1), tap, 0);
+              } else {
+                mbar_arrive_expect_tx(&full_bar[s], (uint32_t)cur_bytes);
+                tma_load_5d(st, &c.a_map[seg], &full_bar[s], c.seg_c0[seg] + ch * kChunkK, x0 + dx, y0 + dy, b, 0);
+                tma_load_4d(st + 2 * kABytes, &c.b_map, &full_bar[s], kc * kChunkK, n0, tap, 0);
+              }
             }
           }
         }
@@ -190,20 +230,20 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
     // ===================== MMA issuer =====================
     uint32_t par = 0;
     int slot = 0, cur_nst = 0, cur_bytes = 0, gg = 0;
-    for (int k = 0;; ++k) {
-      mbar_wait(&q_bar[k & (kMegaQueue - 1)], (uint32_t)(k / kMegaQueue) & 1u);
+    for (int k = 0; rank == 0; ++k) {                    // (pair: the leader issues for both CTAs; the peer's warp 1 only
+      mega_wait_q<kPair>(&q_bar[k & (kMegaQueue - 1)], (uint32_t)(k / kMegaQueue) & 1u);   //  owns its half of the TMEM allocation)
       const int item = item_q[k & (kMegaQueue - 1)];
       if (item < 0) break;
       int L, nt, b, ty, tx;
-      mega_decode(P, item, L, nt, b, ty, tx);
+      mega_decode(P, item, L, nt, b, ty, tx, kPair, 0);
       const TcConvParams& c = P.layer[L].c;
       if (c.nstages != cur_nst || c.stage_bytes != cur_bytes) {
         slot = 0;
         cur_nst = c.nstages;
         cur_bytes = c.stage_bytes;
       }
-      const uint32_t idesc = make_idesc_f16(kTileM, c.bn);
-      const uint32_t b_bytes = (uint32_t)(c.bn * kChunkK * 2);
+      const uint32_t idesc = make_idesc_f16(kPair ? 2 * kTileM : kTileM, c.bn);
+      const uint32_t b_bytes = (uint32_t)((kPair ? c.bn >> 1 : c.bn) * kChunkK * 2);   // rows of B staged by this CTA
       const int total = c.kh * c.kw * (c.seg_chunks[0] + (c.nseg > 1 ? c.seg_chunks[1] : 0));
       const int gsz = c.group_chunks;
       int done = 0;
@@ -223,14 +263,25 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
             const uint32_t sa = smem_u32(stages + (size_t)s * cur_bytes);
             const uint64_t a_hi = make_desc_sw128(sa), a_lo = make_desc_sw128(sa + kABytes);
             const uint64_t b_hi = make_desc_sw128(sa + 2 * kABytes), b_lo = make_desc_sw128(sa + 2 * kABytes + b_bytes);
+            if constexpr (kPair) {
 #pragma unroll
-            for (int k = 0; k < kChunkK / 16; ++k) umma_f16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (!first || k > 0) ? 1u : 0u);
+              for (int k = 0; k < kChunkK / 16; ++k) umma2_f16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (!first || k > 0) ? 1u : 0u);
 #pragma unroll
-            for (int k = 0; k < kChunkK / 16; ++k) umma_f16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+              for (int k = 0; k < kChunkK / 16; ++k) umma2_f16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
 #pragma unroll
-            for (int k = 0; k < kChunkK / 16; ++k) umma_f16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
-            umma_commit(&empty_bar[s]);                      // frees the smem slot once these MMAs retire
-            if (done == gend - 1) umma_commit(&acc_full[buf]);   // group complete -> promotion warps
+              for (int k = 0; k < kChunkK / 16; ++k) umma2_f16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+              umma2_commit(&empty_bar[s]);                     // frees the slot in BOTH CTAs once these MMAs retire
+              if (done == gend - 1) umma2_commit(&acc_full[buf]);   // group complete -> promotion warps of both CTAs
+            } else {
+#pragma unroll
+              for (int k = 0; k < kChunkK / 16; ++k) umma_f16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (!first || k > 0) ? 1u : 0u);
+#pragma unroll
+              for (int k = 0; k < kChunkK / 16; ++k) umma_f16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+#pragma unroll
+              for (int k = 0; k < kChunkK / 16; ++k) umma_f16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+              umma_commit(&empty_bar[s]);                      // frees the smem slot once these MMAs retire
+              if (done == gend - 1) umma_commit(&acc_full[buf]);   // group complete -> promotion warps
+            }
           }
           __syncwarp();
         }
@@ -247,7 +298,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
     const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
     int gg = 0;
     for (int k = 0;; ++k) {
-      mbar_wait(&q_bar[k & (kMegaQueue - 1)], (uint32_t)(k / kMegaQueue) & 1u);
+      mega_wait_q<kPair>(&q_bar[k & (kMegaQueue - 1)], (uint32_t)(k / kMegaQueue) & 1u);
       const int item = item_q[k & (kMegaQueue - 1)];
       if (item < 0) break;
       int L = 0;
@@ -290,7 +341,10 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        if (lane == 0) {
+          if (kPair && rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[buf]), 0));   // the issuer lives in the leader
+          else mbar_arrive(&acc_empty[buf]);
+        }
       }
 
       // ---- epilogue of this item (the issuer is already accumulating the next one) ----
@@ -298,9 +352,11 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
       int nt, b, ty, tx;
       {
         const int mtiles = c.B * c.tiles_y * c.tiles_x;
+        const int units = kPair ? mtiles >> 1 : mtiles;
         const int r = item - ML.item0;
-        nt = r / mtiles;
-        int mt = r - nt * mtiles;
+        nt = r / units;
+        int mt = r - nt * units;
+        if (kPair) mt = 2 * mt + rank;
         tx = mt % c.tiles_x;
         mt /= c.tiles_x;
         ty = mt % c.tiles_y;
@@ -366,8 +422,13 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512u);
+  if constexpr (kPair) {
+    cluster_sync_all();                  // no CTA leaves (or frees TMEM) while its peer may still signal it
+    if (warp == 1) tmem2_dealloc(tmem_base, 512u);
+  } else {
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512u);
+  }
 #endif
 }
 
@@ -380,10 +441,12 @@ struct MegaPlan {
   MegaParams P;
   int pos_of_layer[32];          // tensor-core layer id -> position in P.layer (-1: not planned)
   int nflags;
+  int pair;                      // 1: items are tile pairs for update_mega_kernel<true> (set before the layers are added)
   MegaPlan() {
     memset(&P, 0, sizeof(P));
     for (int i = 0; i < 32; ++i) pos_of_layer[i] = -1;
     nflags = 0;
+    pair = 0;
   }
 };
 
@@ -395,6 +458,8 @@ inline int mega_add(MegaPlan& M, int layer_id, TcConvParams& p, int n_tiles_n, c
   if (p.bn % 16 != 0 || p.bn < 16 || p.bn > 256 || p.TW * p.TH != kTileM) return RAFT_ERR_BAD_SHAPE;
   if (p.mode != EPI_LINEAR && p.mode != EPI_GRU_ZR && p.mode != EPI_GRU_Q) return RAFT_ERR_UNSUPPORTED;
   if (p.stride < 1) p.stride = 1;
+  p.pair = M.pair;
+  if (M.pair && (p.bn < 32 || ((p.B * ceil_div(p.H, p.TH) * ceil_div(p.W, p.TW)) & 1))) return RAFT_ERR_BAD_SHAPE;
   const int saved_mode = p.mode;
   p.mode = EPI_GRU_Q;                      // reserve the transposition patches whatever the layer's mode (one smem layout)
   tc_finalize(p);
@@ -420,7 +485,7 @@ inline int mega_add(MegaPlan& M, int layer_id, TcConvParams& p, int n_tiles_n, c
   if (ML.dep_ry < 1) ML.dep_ry = 1;
   if (ML.dep_rx < 1) ML.dep_rx = 1;
   M.pos_of_layer[layer_id] = M.P.nlayers;
-  M.P.nitems += mtiles * n_tiles_n;
+  M.P.nitems += (M.pair ? mtiles / 2 : mtiles) * n_tiles_n;
   M.nflags += mtiles * n_tiles_n;
   ++M.P.nlayers;
   return RAFT_OK;
@@ -435,16 +500,36 @@ inline int mega_launch(MegaPlan& M, unsigned int* flags, size_t flag_words, bool
   RAFT_CUDA_TRY(cudaGetDevice(&dev));
   static unsigned long long attr_mask = 0;          // per-device attribute (benign race: idempotent)
   if (!(attr_mask & (1ull << (dev & 63)))) {
-    RAFT_CUDA_TRY(cudaFuncSetAttribute(update_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    RAFT_CUDA_TRY(cudaFuncSetAttribute(update_mega_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    RAFT_CUDA_TRY(cudaFuncSetAttribute(update_mega_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_mask |= 1ull << (dev & 63);
   }
   if (zero_flags) RAFT_CUDA_TRY(cudaMemsetAsync(flags, 0, ((size_t)M.nflags + 1) * sizeof(unsigned int), stream));
-  // All CTAs must be co-resident (items wait on items of other CTAs): one CTA per SM, never more CTAs than SMs.
+  // Items wait on items claimed by other CTAs: every claimed item is held by a RUNNING CTA, so the wait graph is acyclic
+  // whatever the number of co-resident CTAs; one CTA per SM (shared memory), never more CTAs than SMs.
   static int num_sms[64] = {0};
   if (!num_sms[dev & 63]) RAFT_CUDA_TRY(cudaDeviceGetAttribute(&num_sms[dev & 63], cudaDevAttrMultiProcessorCount, dev));
-  const int grid = M.P.nitems < num_sms[dev & 63] ? M.P.nitems : num_sms[dev & 63];
   const int smem = kSmemBudget + 1024;
-  update_mega_kernel<<<grid, kMegaThreads, smem, stream>>>(M.P);
+  if (!M.pair) {
+    const int grid = M.P.nitems < num_sms[dev & 63] ? M.P.nitems : num_sms[dev & 63];
+    update_mega_kernel<false><<<grid, kMegaThreads, smem, stream>>>(M.P);
+    return raft_launch_status();
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  const int pairs = M.P.nitems < num_sms[dev & 63] / 2 ? M.P.nitems : num_sms[dev & 63] / 2;
+  cfg.gridDim = dim3((unsigned)(2 * pairs));
+  cfg.blockDim = dim3((unsigned)kMegaThreads);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  RAFT_CUDA_TRY(cudaLaunchKernelEx(&cfg, update_mega_kernel<true>, M.P));
   return raft_launch_status();
 }
 

@@ -273,10 +273,14 @@ inline int launch_tc_layer(const UpdateCtx& c, int layer, int nseg, const TcSeg*
   if (chunks * kChunkK != L.cin_pad) return RAFT_ERR_BAD_SHAPE;
   const __half* whi = reinterpret_cast<const __half*>(c.prepared + c.PL.tc_hi[layer]);
   const __half* wlo = reinterpret_cast<const __half*>(c.prepared + c.PL.tc_lo[layer]);
-  RAFT_TRY(make_tmap_wgt2(&p.b_map, whi, wlo, L.kh * L.kw, L.cout_pad, L.cin_pad, L.bn));
+  // pair plan (update_mega_kernel<true>): each CTA of a pair stages half of the weight rows; the pair's N is at least 32
+  // (rows past cout_pad are out of bounds of the map and arrive as zeros)
+  const bool pair = c.plan && c.plan->pair;
+  const int bn = pair && L.bn < 32 ? 32 : L.bn;
+  RAFT_TRY(make_tmap_wgt2(&p.b_map, whi, wlo, L.kh * L.kw, L.cout_pad, L.cin_pad, pair ? bn / 2 : bn));
   p.kh = L.kh; p.kw = L.kw; p.ph = (L.kh - 1) / 2; p.pw = (L.kw - 1) / 2;
   p.B = c.B; p.H = c.h; p.W = c.w; p.TH = th; p.TW = tw;
-  p.bn = L.bn;
+  p.bn = bn;
   p.bias = reinterpret_cast<const float*>(c.prepared + c.PL.tc_bias[layer]);
   p.inv_scale = reinterpret_cast<const float*>(c.prepared + c.PL.tc_scale[layer]) + 1;
   if (p.out_scale == 0.0f) p.out_scale = 1.0f;

@@ -20,44 +20,11 @@ struct alignas(64) PairParams {
 };
 
 #if defined(__CUDA_ARCH__)
-__device__ __forceinline__ uint32_t cluster_rank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-  return r;
-}
 __device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* m, uint32_t leader_bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1)
       : "memory");
-}
-__device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                   smem_u32(bar)),
-               "h"(mask)
-               : "memory");
-}
-__device__ __forceinline__ void tmem2_alloc(uint32_t* holder, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(holder)), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tmem2_relinquish() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem2_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 #endif
 
@@ -72,7 +39,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1) pair_kernel(
   uint64_t* acc_full = empty_bar + kStages;
   uint32_t* holder = reinterpret_cast<uint32_t*>(acc_full + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_rank();
+  const uint32_t rank = cluster_ctarank();
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -96,7 +63,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1) pair_kernel(
       for (int kc = 0; kc < chunks; ++kc) {
         const int s = kc % kStages;
         mbar_wait(&empty_bar[s], ((uint32_t)(kc / kStages) & 1u) ^ 1u);
-        const uint32_t lead = mapa_rank(smem_u32(&full_bar[s]), 0);
+        const uint32_t lead = mapa_u32(smem_u32(&full_bar[s]), 0);
         if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(2 * stage_bytes));   // bytes of BOTH CTAs
         uint8_t* st = smem + (size_t)s * stage_bytes;
         tma2_load_2d(st, &p.a_map, lead, kc * 64, (int)rank * 128);
@@ -115,8 +82,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1) pair_kernel(
           const uint64_t ad = make_desc_sw128(sa), bd = make_desc_sw128(sa + a_bytes);
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma2_f16(tmem_base, ad + 2 * k, bd + 2 * k, idesc, (kc > 0 || k > 0) ? 1u : 0u);
-          umma2_commit_mc(&empty_bar[s], 3);
-          if (kc == chunks - 1) umma2_commit_mc(acc_full, 3);
+          umma2_commit(&empty_bar[s]);
+          if (kc == chunks - 1) umma2_commit(acc_full);
         }
         __syncwarp();
       }
@@ -142,7 +109,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1) pair_kernel(
 
 int main() {
   int bad_total = 0;
-  for (int n : {256, 128, 192, 64, 16}) {
+  for (int n : {256, 128, 192, 96, 64, 32, 16}) {
     std::vector<__half> ha((size_t)kM * kK), hb((size_t)n * kK);
     std::vector<float> fa(ha.size()), fb(hb.size());
     srand(1234 + n);

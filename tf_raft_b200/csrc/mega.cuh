@@ -42,7 +42,9 @@ struct alignas(64) MegaParams {
   int nlayers, nitems;
   unsigned int* flags;            // zeroed before the launch
   unsigned int* next_item;        // work-list cursor (zeroed with the flags): CTAs claim items with atomicAdd
+  long long* dbg;                 // optional schedule trace (tools/timeline_mega.py): [CTA][kMegaDbgItems][8] globaltimer stamps
 };
+constexpr int kMegaDbgItems = 16;
 constexpr int kMegaQueue = 16;    // per-CTA ring of claimed item numbers (producer -> issuer / epilogue warps)
 
 #if defined(__CUDA_ARCH__)
@@ -55,6 +57,17 @@ __device__ __forceinline__ void red_release_gpu_add(unsigned int* p, unsigned in
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// schedule trace: compiled in only with -DRAFT_MEGA_TRACE (tools/timeline_mega.py loads such a build through RAFT_B200_LIB)
+#ifdef RAFT_MEGA_TRACE
+#define MEGA_STAMP(i) do { if (dbg) dbg[i] = global_ns(); } while (0)
+#else
+#define MEGA_STAMP(i) do { } while (0)
+#endif
+__device__ __forceinline__ long long global_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 template <bool kPair>
 __device__ __forceinline__ void mega_wait_q(uint64_t* bar, uint32_t parity) {     // item-number queue: filled by the leader CTA
@@ -116,6 +129,12 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
     for (int i = 0; i < kMegaQueue; ++i) mbar_init(&q_bar[i], 1);
     fence_mbar_init();
   }
+  if (warp == 2 && lane < P.nlayers) {                   // descriptor fetches off the first stage of every layer
+    const TcConvParams& c = P.layer[lane].c;
+    prefetch_tmap(&c.a_map[0]);
+    if (c.nseg > 1) prefetch_tmap(&c.a_map[1]);
+    prefetch_tmap(&c.b_map);
+  }
   if (warp == 1) {
     if constexpr (kPair) {
       tmem2_alloc(tmem_holder, 512u);
@@ -156,6 +175,10 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
           if (item < 0) item = P.nitems;
         }
         if (item >= P.nitems) break;
+#ifdef RAFT_MEGA_TRACE
+        long long* dbg = (P.dbg && k < kMegaDbgItems) ? P.dbg + ((size_t)blockIdx.x * kMegaDbgItems + k) * 8 : nullptr;
+        if (dbg) { dbg[0] = item + 1; dbg[1] = global_ns(); }
+#endif
         int nxt = P.nitems;
         int L, nt, b, ty, tx;
         mega_decode(P, item, L, nt, b, ty, tx, kPair, rank);
@@ -183,6 +206,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
           }
           fence_proxy_async_all();          // acquired generic-proxy writes -> visible to the TMA loads issued below
         }
+        MEGA_STAMP(2);
         // ---- ring geometry: a layer with another stage size re-carves the ring once it has drained ----
         if (c.nstages != cur_nst || c.stage_bytes != cur_bytes) {
           for (int s = 0; s < kMegaMaxStages; ++s)
@@ -192,10 +216,38 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
           cur_nst = c.nstages;
           cur_bytes = c.stage_bytes;
         }
+        MEGA_STAMP(3);
         const int ntaps = c.kh * c.kw;
         const int x0 = tx * c.TW * c.stride, y0 = ty * c.TH * c.stride, n0 = nt * c.bn;
         int left = ntaps * (c.seg_chunks[0] + (c.nseg > 1 ? c.seg_chunks[1] : 0));
-        for (int tap = 0; tap < ntaps; ++tap) {
+        if constexpr (kPair) {
+          if (c.kstage == 2) {           // two K chunks per stage: two activation boxes, ONE weight box (pair form only)
+            const int per_tap = c.seg_chunks[0] + (c.nseg > 1 ? c.seg_chunks[1] : 0);
+            for (int tap = 0; tap < ntaps; ++tap) {
+              const int dy = tap / c.kw - c.ph, dx = tap % c.kw - c.pw;
+              for (int kc = 0; kc < per_tap; kc += 2) {
+                left -= 2;
+                if (left == 0 && rank == 0) nxt = (int)atomicAdd(P.next_item, 1u);
+                const int s = slot;
+                slot = slot + 1 == cur_nst ? 0 : slot + 1;
+                mbar_wait(&empty_bar[s], ((par >> s) & 1u) ^ 1u);
+                par ^= 1u << s;
+                used |= 1u << s;
+                uint8_t* st = stages + (size_t)s * cur_bytes;
+                if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(2 * cur_bytes));
+                const uint32_t lead = mapa_u32(smem_u32(&full_bar[s]), 0);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                  const int kj = kc + j, seg = kj < c.seg_chunks[0] ? 0 : 1, ch = seg ? kj - c.seg_chunks[0] : kj;
+                  tma2_load_5d(st + j * 2 * kABytes, &c.a_map[seg], lead, c.seg_c0[seg] + ch * kChunkK, x0 + dx, y0 + dy, b, 0);
+                }
+                tma2_load_5d(st + 4 * kABytes, &c.b_map, lead, 0, n0 + rank * (c.bn >> 1), tap, 0, kc);
+              }
+            }
+            left = -1;                   // (the single-chunk loop below is skipped)
+          }
+        }
+        for (int tap = 0; left > 0 && tap < ntaps; ++tap) {
           const int dy = tap / c.kw - c.ph, dx = tap % c.kw - c.pw;
           int kc = 0;
           for (int seg = 0; seg < c.nseg; ++seg) {
@@ -223,6 +275,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
             }
           }
         }
+        MEGA_STAMP(4);
         item = nxt;
       }
     }
@@ -259,6 +312,28 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
           mbar_wait(&full_bar[s], (par >> s) & 1u);
           par ^= 1u << s;
           tc_fence_after();
+          if (kPair && c.kstage == 2) {      // the stage holds the group's two chunks: [A k | A k+1 | B k | B k+1]
+            if (elect_one()) {
+              const uint32_t sa = smem_u32(stages + (size_t)s * cur_bytes);
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const uint64_t a_hi = make_desc_sw128(sa + j * 2 * kABytes), a_lo = make_desc_sw128(sa + j * 2 * kABytes + kABytes);
+                const uint64_t b_hi = make_desc_sw128(sa + 4 * kABytes + j * 2 * b_bytes),
+                               b_lo = make_desc_sw128(sa + 4 * kABytes + j * 2 * b_bytes + b_bytes);
+#pragma unroll
+                for (int k = 0; k < kChunkK / 16; ++k) umma2_f16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (j > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+                for (int k = 0; k < kChunkK / 16; ++k) umma2_f16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+#pragma unroll
+                for (int k = 0; k < kChunkK / 16; ++k) umma2_f16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+              }
+              umma2_commit(&empty_bar[s]);
+              umma2_commit(&acc_full[buf]);
+            }
+            __syncwarp();
+            ++done;                            // (the loop header adds the second chunk)
+            continue;
+          }
           if (elect_one()) {
             const uint32_t sa = smem_u32(stages + (size_t)s * cur_bytes);
             const uint64_t a_hi = make_desc_sw128(sa), a_lo = make_desc_sw128(sa + kABytes);
@@ -318,11 +393,15 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
 #pragma unroll
         for (int j = 0; j < 32; ++j) racc[ci][j] = 0.0f;
 
+#ifdef RAFT_MEGA_TRACE
+      long long* dbg = (P.dbg && k < kMegaDbgItems && warp == 2 && lane == 0) ? P.dbg + ((size_t)blockIdx.x * kMegaDbgItems + k) * 8 : nullptr;
+#endif
 #pragma unroll 1
       for (int g = 0; g < ngroups; ++g, ++gg) {
         const int buf = gg & 1;
         mbar_wait(&acc_full[buf], (uint32_t)(gg >> 1) & 1u);
         tc_fence_after();
+        if (g == 0) MEGA_STAMP(5);
 #pragma unroll
         for (int ci = 0; ci < kMaxCh; ++ci) {
           if (ci < my_chunks) {
@@ -347,6 +426,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
         }
       }
 
+      MEGA_STAMP(6);
       // ---- epilogue of this item (the issuer is already accumulating the next one) ----
       // (tile coordinates are decoded here, not before the promotion loop: 64 accumulators leave few registers to carry them)
       int nt, b, ty, tx;
@@ -418,6 +498,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
         const int mtiles = c.B * c.tiles_y * c.tiles_x;
         red_release_gpu_add(P.flags + ML.flag0 + nt * mtiles + (b * c.tiles_y + ty) * c.tiles_x + tx, 1u);
       }
+      MEGA_STAMP(7);
     }
   }
 
@@ -431,6 +512,9 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
   }
 #endif
 }
+
+extern int g_dbg_layer;            // timeline debugging (raft_b200_debug_timeline, api.cu)
+extern long long* g_dbg_buf;
 
 // ------------------------------------------------------------------------------------------------
 // Host side: the plan of one update-block application.
@@ -465,6 +549,7 @@ inline int mega_add(MegaPlan& M, int layer_id, TcConvParams& p, int n_tiles_n, c
   tc_finalize(p);
   p.mode = saved_mode;
   if (p.nstages < 2) return RAFT_ERR_UNSUPPORTED;
+  if (p.kstage == 2 && (!M.pair || p.group_chunks != 2 || p.bn > 128)) return RAFT_ERR_UNSUPPORTED;   // a stage = one promotion group
   if (p.nstages > kMegaMaxStages) p.nstages = kMegaMaxStages;
   p.n_tiles_n = n_tiles_n;
   p.pdl = 0;
@@ -496,6 +581,7 @@ inline int mega_launch(MegaPlan& M, unsigned int* flags, size_t flag_words, bool
   if ((size_t)M.nflags + 1 > flag_words) return RAFT_ERR_WORKSPACE;
   M.P.flags = flags;
   M.P.next_item = flags + M.nflags;
+  M.P.dbg = g_dbg_layer == 3000 ? g_dbg_buf : nullptr;      // raft_b200_debug_timeline(3000, buf of 148 * 16 * 8 int64)
   int dev = 0;
   RAFT_CUDA_TRY(cudaGetDevice(&dev));
   static unsigned long long attr_mask = 0;          // per-device attribute (benign race: idempotent)

@@ -85,9 +85,6 @@ struct alignas(64) TcConvParams {
   // update_mega_kernel<true> only: the tile is one half of a CTA pair's M = 256 MMA; a stage holds this CTA's 128 activation
   // rows and HALF of the bn weight rows (b_map's box is bn / 2 rows).
   int pair;
-  // ... and, for layers of at most 128 columns: a stage holds TWO K chunks (one promotion group) -- two activation boxes and
-  // ONE weight box (make_tmap_wgt2k); kstage = chunks per stage (1 or 2).
-  int kstage;
 };
 
 #if defined(__CUDA_ARCH__)
@@ -720,7 +717,7 @@ inline void tc_pick_tile(int W, int H, int* tw, int* th) {
 inline int tc_finalize(TcConvParams& p) {
   p.tiles_x = ceil_div(p.W, p.TW);
   p.tiles_y = ceil_div(p.H, p.TH);
-  p.stage_bytes = (p.kstage == 2 ? 2 : 1) * (2 * kABytes + 2 * (p.pair ? p.bn / 2 : p.bn) * kChunkK * 2);
+  p.stage_bytes = 2 * kABytes + 2 * (p.pair ? p.bn / 2 : p.bn) * kChunkK * 2;
   if (p.row3) p.stage_bytes = kARow3Bytes + 3 * 2 * p.bn * kChunkK * 2;
   const int patch = tc_uses_patch(p.mode) ? kEpiPatchBytes : 0;   // 16 x 2 KB patches (GRU q)
   int nst = (kSmemBudget - patch) / p.stage_bytes;

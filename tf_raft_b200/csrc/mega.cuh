@@ -220,34 +220,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
         const int ntaps = c.kh * c.kw;
         const int x0 = tx * c.TW * c.stride, y0 = ty * c.TH * c.stride, n0 = nt * c.bn;
         int left = ntaps * (c.seg_chunks[0] + (c.nseg > 1 ? c.seg_chunks[1] : 0));
-        if constexpr (kPair) {
-          if (c.kstage == 2) {           // two K chunks per stage: two activation boxes, ONE weight box (pair form only)
-            const int per_tap = c.seg_chunks[0] + (c.nseg > 1 ? c.seg_chunks[1] : 0);
-            for (int tap = 0; tap < ntaps; ++tap) {
-              const int dy = tap / c.kw - c.ph, dx = tap % c.kw - c.pw;
-              for (int kc = 0; kc < per_tap; kc += 2) {
-                left -= 2;
-                if (left == 0 && rank == 0) nxt = (int)atomicAdd(P.next_item, 1u);
-                const int s = slot;
-                slot = slot + 1 == cur_nst ? 0 : slot + 1;
-                mbar_wait(&empty_bar[s], ((par >> s) & 1u) ^ 1u);
-                par ^= 1u << s;
-                used |= 1u << s;
-                uint8_t* st = stages + (size_t)s * cur_bytes;
-                if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(2 * cur_bytes));
-                const uint32_t lead = mapa_u32(smem_u32(&full_bar[s]), 0);
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                  const int kj = kc + j, seg = kj < c.seg_chunks[0] ? 0 : 1, ch = seg ? kj - c.seg_chunks[0] : kj;
-                  tma2_load_5d(st + j * 2 * kABytes, &c.a_map[seg], lead, c.seg_c0[seg] + ch * kChunkK, x0 + dx, y0 + dy, b, 0);
-                }
-                tma2_load_5d(st + 4 * kABytes, &c.b_map, lead, 0, n0 + rank * (c.bn >> 1), tap, 0, kc);
-              }
-            }
-            left = -1;                   // (the single-chunk loop below is skipped)
-          }
-        }
-        for (int tap = 0; left > 0 && tap < ntaps; ++tap) {
+        for (int tap = 0; tap < ntaps; ++tap) {
           const int dy = tap / c.kw - c.ph, dx = tap % c.kw - c.pw;
           int kc = 0;
           for (int seg = 0; seg < c.nseg; ++seg) {
@@ -312,28 +285,6 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
           mbar_wait(&full_bar[s], (par >> s) & 1u);
           par ^= 1u << s;
           tc_fence_after();
-          if (kPair && c.kstage == 2) {      // the stage holds the group's two chunks: [A k | A k+1 | B k | B k+1]
-            if (elect_one()) {
-              const uint32_t sa = smem_u32(stages + (size_t)s * cur_bytes);
-#pragma unroll
-              for (int j = 0; j < 2; ++j) {
-                const uint64_t a_hi = make_desc_sw128(sa + j * 2 * kABytes), a_lo = make_desc_sw128(sa + j * 2 * kABytes + kABytes);
-                const uint64_t b_hi = make_desc_sw128(sa + 4 * kABytes + j * 2 * b_bytes),
-                               b_lo = make_desc_sw128(sa + 4 * kABytes + j * 2 * b_bytes + b_bytes);
-#pragma unroll
-                for (int k = 0; k < kChunkK / 16; ++k) umma2_f16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (j > 0 || k > 0) ? 1u : 0u);
-#pragma unroll
-                for (int k = 0; k < kChunkK / 16; ++k) umma2_f16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
-#pragma unroll
-                for (int k = 0; k < kChunkK / 16; ++k) umma2_f16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
-              }
-              umma2_commit(&empty_bar[s]);
-              umma2_commit(&acc_full[buf]);
-            }
-            __syncwarp();
-            ++done;                            // (the loop header adds the second chunk)
-            continue;
-          }
           if (elect_one()) {
             const uint32_t sa = smem_u32(stages + (size_t)s * cur_bytes);
             const uint64_t a_hi = make_desc_sw128(sa), a_lo = make_desc_sw128(sa + kABytes);
@@ -549,7 +500,6 @@ inline int mega_add(MegaPlan& M, int layer_id, TcConvParams& p, int n_tiles_n, c
   tc_finalize(p);
   p.mode = saved_mode;
   if (p.nstages < 2) return RAFT_ERR_UNSUPPORTED;
-  if (p.kstage == 2 && (!M.pair || p.group_chunks != 2 || p.bn > 128)) return RAFT_ERR_UNSUPPORTED;   // a stage = one promotion group
   if (p.nstages > kMegaMaxStages) p.nstages = kMegaMaxStages;
   p.n_tiles_n = n_tiles_n;
   p.pdl = 0;

@@ -71,19 +71,6 @@ inline int make_tmap_wgt2(CUtensorMap* out, const __half* hi, const __half* lo, 
   return make_tmap_f16(out, hi, 4, dims, str, box);
 }
 
-// Weight planes, TWO consecutive 64-channel K chunks per box: rank-5 map (64, cout_pad, taps, plane, chunk) whose last
-// dimension steps 128 bytes along cin; box {64, bn, 1, 2, 2} -> smem [chunk k: hi bn rows | lo bn rows][chunk k+1: hi | lo].
-// (One box instead of two: the layers with few output columns are bound by the number of TMA boxes, not by their bytes.)
-inline int make_tmap_wgt2k(CUtensorMap* out, const __half* hi, const __half* lo, int taps, int cout_pad, int cin_pad,
-                           int bn) {
-  const ptrdiff_t pstride = reinterpret_cast<const char*>(lo) - reinterpret_cast<const char*>(hi);
-  if (pstride <= 0 || (pstride & 15) || cin_pad % 128 != 0) return RAFT_ERR_BAD_ARG;
-  uint64_t dims[5] = {64, (uint64_t)cout_pad, (uint64_t)taps, 2, (uint64_t)(cin_pad / 64)};
-  uint64_t str[4] = {(uint64_t)cin_pad * 2, (uint64_t)cout_pad * cin_pad * 2, (uint64_t)pstride, 128};
-  uint32_t box[5] = {64, (uint32_t)bn, 1, 2, 2};
-  return make_tmap_f16(out, hi, 5, dims, str, box);
-}
-
 // Weight planes, three taps (one kernel row) per box: box {64, bn, 3, 2} -> smem [hi: tap 0 | tap 1 | tap 2][lo: ...].
 inline int make_tmap_wgt3(CUtensorMap* out, const __half* hi, const __half* lo, int taps, int cout_pad, int cin_pad,
                           int bn) {

@@ -277,10 +277,7 @@ inline int launch_tc_layer(const UpdateCtx& c, int layer, int nseg, const TcSeg*
   // (rows past cout_pad are out of bounds of the map and arrive as zeros)
   const bool pair = c.plan && c.plan->pair;
   const int bn = pair && L.bn < 32 ? 32 : L.bn;
-  // ... and layers of at most 128 columns with an even number of K chunks per tap take two chunks per stage (one weight box)
-  p.kstage = pair && bn <= 128 && chunks % 2 == 0 ? 2 : 1;
-  if (p.kstage == 2) RAFT_TRY(make_tmap_wgt2k(&p.b_map, whi, wlo, L.kh * L.kw, L.cout_pad, L.cin_pad, bn / 2));
-  else RAFT_TRY(make_tmap_wgt2(&p.b_map, whi, wlo, L.kh * L.kw, L.cout_pad, L.cin_pad, pair ? bn / 2 : bn));
+  RAFT_TRY(make_tmap_wgt2(&p.b_map, whi, wlo, L.kh * L.kw, L.cout_pad, L.cin_pad, pair ? bn / 2 : bn));
   p.kh = L.kh; p.kw = L.kw; p.ph = (L.kh - 1) / 2; p.pw = (L.kw - 1) / 2;
   p.B = c.B; p.H = c.h; p.W = c.w; p.TH = th; p.TW = tw;
   p.bn = bn;

@@ -24,8 +24,12 @@ namespace raft {
 
 constexpr int kMegaMaxLayers = 14;
 constexpr int kMegaEpiWarps = 16;
-constexpr int kMegaThreads = 64 + 32 * kMegaEpiWarps + 32;   // + the weight producer (last warp)
-constexpr int kMegaWgtWarp = 2 + kMegaEpiWarps;
+// TMA-issuing warps.  MEASURED (tools/tma_probe3.cu, profiles/r02_tma_probe_issuers.log): ONE issuing thread gets one box per
+// ~770-815 cycles whatever the box (16-64 KB, rank 2-5, 2-8 boxes in flight); two threads of different warps get two, three
+// get ~2.7 (the SM's ingest limit, ~78 B/clk).  The stages of an item are therefore dealt round-robin to kMegaProducers
+// producer warps (warp 0 and the warps after the epilogue warps); each issues both boxes of its stages.
+constexpr int kMegaProducers = 2;
+constexpr int kMegaThreads = 64 + 32 * kMegaEpiWarps + 32 * (kMegaProducers - 1);
 constexpr int kMegaMaxStages = 8;
 
 struct alignas(64) MegaLayer {
@@ -120,7 +124,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kMegaMaxStages; ++s) {
-      mbar_init(&full_bar[s], 2);                       // activation producer + weight producer
+      mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -150,19 +154,22 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
-  if (warp == 0) {
-    // ===================== TMA producer =====================
+  if (warp == 0 || warp >= 2 + kMegaEpiWarps) {
+    // ===================== TMA producers =====================
+    const int pid = warp == 0 ? 0 : warp - (2 + kMegaEpiWarps) + 1;       // this warp issues the stages seq % kMegaProducers == pid
+    const bool claimer = rank == 0 && pid == 0;                            // ... and one of them claims the items
     if (elect_one()) {
       uint32_t par = 0, used = 0;          // per ring slot: parity of its use count, used since the last drain
       int slot = 0, cur_nst = 0, cur_bytes = 0;
+      unsigned int seq = 0;                // stages since the start of the kernel (every producer counts all of them)
       // Items are CLAIMED, not pre-assigned: a CTA that becomes free takes the lowest unclaimed item of the list (layer
       // order = priority order), so no CTA sits on a blocked item while a runnable one waits behind it in a fixed
       // per-CTA sequence.  Every dependency points to a lower item number, which some co-resident CTA has already claimed,
       // so the wait graph stays acyclic.  The claimed number is handed to the other roles through item_q / q_bar.
-      int item = rank == 0 ? (int)atomicAdd(P.next_item, 1u) : 0;
+      int item = claimer ? (int)atomicAdd(P.next_item, 1u) : 0;
       for (int k = 0;; ++k) {
         const int qs = k & (kMegaQueue - 1);
-        if (rank == 0) {
+        if (claimer) {
           const int pub = item < P.nitems ? item : -1;
           item_q[qs] = pub;
           mbar_arrive(&q_bar[qs]);                       // (release: the slot's item number is visible to the waiters)
@@ -177,7 +184,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
         }
         if (item >= P.nitems) break;
 #ifdef RAFT_MEGA_TRACE
-        long long* dbg = (P.dbg && k < kMegaDbgItems) ? P.dbg + ((size_t)blockIdx.x * kMegaDbgItems + k) * 8 : nullptr;
+        long long* dbg = (P.dbg && pid == 0 && k < kMegaDbgItems) ? P.dbg + ((size_t)blockIdx.x * kMegaDbgItems + k) * 8 : nullptr;
         if (dbg) { dbg[0] = item + 1; dbg[1] = global_ns(); }
 #endif
         int nxt = P.nitems;
@@ -219,7 +226,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
         }
         MEGA_STAMP(3);
         const int ntaps = c.kh * c.kw;
-        const int x0 = tx * c.TW * c.stride, y0 = ty * c.TH * c.stride;
+        const int x0 = tx * c.TW * c.stride, y0 = ty * c.TH * c.stride, n0 = nt * c.bn;
         int left = ntaps * (c.seg_chunks[0] + (c.nseg > 1 ? c.seg_chunks[1] : 0));
         for (int tap = 0; tap < ntaps; ++tap) {
           const int dy = tap / c.kw - c.ph, dx = tap % c.kw - c.pw;
@@ -228,21 +235,25 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
             for (int ch = 0; ch < c.seg_chunks[seg]; ++ch, ++kc) {
               // claim the next item while the last stage of this one is still to be loaded: late enough that the CTA is
               // about to be free, early enough that the atomic's round trip hides behind the slot wait below
-              if (--left == 0 && rank == 0) nxt = (int)atomicAdd(P.next_item, 1u);
+              if (--left == 0 && claimer) nxt = (int)atomicAdd(P.next_item, 1u);
               const int s = slot;
               slot = slot + 1 == cur_nst ? 0 : slot + 1;
-              mbar_wait(&empty_bar[s], ((par >> s) & 1u) ^ 1u);
-              par ^= 1u << s;
+              const bool mine = seq++ % kMegaProducers == (unsigned)pid;
+              if (mine) mbar_wait(&empty_bar[s], ((par >> s) & 1u) ^ 1u);
+              par ^= 1u << s;                                // (every producer tracks the use count of every slot)
               used |= 1u << s;
+              if (!mine) continue;
               uint8_t* st = stages + (size_t)s * cur_bytes;
               if constexpr (kPair) {
-                // both CTAs' boxes complete on the LEADER's barrier, which expects the bytes of both CTAs
-                if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(2 * 2 * kABytes));
+                // both CTAs' boxes complete on the LEADER's barrier, which expects the bytes of both stages
+                if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(2 * cur_bytes));
                 const uint32_t lead = mapa_u32(smem_u32(&full_bar[s]), 0);
                 tma2_load_5d(st, &c.a_map[seg], lead, c.seg_c0[seg] + ch * kChunkK, x0 + dx, y0 + dy, b, 0);
+                tma2_load_4d(st + 2 * kABytes, &c.b_map, lead, kc * kChunkK, n0 + rank * (c.bn >> 1), tap, 0);
               } else {
-                mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(2 * kABytes));
+                mbar_arrive_expect_tx(&full_bar[s], (uint32_t)cur_bytes);
                 tma_load_5d(st, &c.a_map[seg], &full_bar[s], c.seg_c0[seg] + ch * kChunkK, x0 + dx, y0 + dy, b, 0);
+                tma_load_4d(st + 2 * kABytes, &c.b_map, &full_bar[s], kc * kChunkK, n0, tap, 0);
               }
             }
           }
@@ -311,52 +322,6 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
           __syncwarp();
         }
         ++gg;
-      }
-    }
-  } else if (warp == kMegaWgtWarp) {
-    // ===================== weight producer =====================
-    // MEASURED (tools/tma_probe3.cu, profiles/r02_tma_probe_issuers.log): ONE issuing thread gets one TMA box per ~770-815
-    // cycles whatever the box (16-64 KB, rank 2-5, 2-8 boxes in flight); two threads of different warps get two.  The
-    // activation and the weight box of a stage are therefore issued by different warps.  This warp follows the same item
-    // queue and the same ring bookkeeping as the activation producer; weights have no dependencies.
-    if (elect_one()) {
-      uint32_t par = 0, used = 0;
-      int slot = 0, cur_nst = 0, cur_bytes = 0;
-      for (int k = 0;; ++k) {
-        mega_wait_q<kPair>(&q_bar[k & (kMegaQueue - 1)], (uint32_t)(k / kMegaQueue) & 1u);
-        const int item = item_q[k & (kMegaQueue - 1)];
-        if (item < 0) break;
-        int L, nt, b, ty, tx;
-        mega_decode(P, item, L, nt, b, ty, tx, kPair, rank);
-        const TcConvParams& c = P.layer[L].c;
-        if (c.nstages != cur_nst || c.stage_bytes != cur_bytes) {
-          for (int s = 0; s < kMegaMaxStages; ++s)
-            if ((used >> s) & 1u) mbar_wait(&empty_bar[s], ((par >> s) & 1u) ^ 1u);
-          used = 0;
-          slot = 0;
-          cur_nst = c.nstages;
-          cur_bytes = c.stage_bytes;
-        }
-        const int ntaps = c.kh * c.kw, n0 = nt * c.bn;
-        const int per_tap = c.seg_chunks[0] + (c.nseg > 1 ? c.seg_chunks[1] : 0);
-        const uint32_t wbytes = (uint32_t)(cur_bytes - 2 * kABytes);
-        for (int tap = 0; tap < ntaps; ++tap) {
-          for (int kc = 0; kc < per_tap; ++kc) {
-            const int s = slot;
-            slot = slot + 1 == cur_nst ? 0 : slot + 1;
-            mbar_wait(&empty_bar[s], ((par >> s) & 1u) ^ 1u);
-            par ^= 1u << s;
-            used |= 1u << s;
-            uint8_t* st = stages + (size_t)s * cur_bytes + 2 * kABytes;
-            if constexpr (kPair) {
-              if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * wbytes);
-              tma2_load_4d(st, &c.b_map, mapa_u32(smem_u32(&full_bar[s]), 0), kc * kChunkK, n0 + rank * (c.bn >> 1), tap, 0);
-            } else {
-              mbar_arrive_expect_tx(&full_bar[s], wbytes);
-              tma_load_4d(st, &c.b_map, &full_bar[s], kc * kChunkK, n0, tap, 0);
-            }
-          }
-        }
       }
     }
   } else {

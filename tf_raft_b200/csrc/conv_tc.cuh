@@ -503,11 +503,21 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarpsConv, 1) conv_tc_kernel(con
                 mbar_wait(&empty_bar[s], phase ^ 1u);
                 if (p.dbg && blockIdx.x == 0 && it < 512) p.dbg[it] = clock64();              // slot free
                 uint8_t* st = stages + (size_t)s * p.stage_bytes;
-                if (it >= npre) mbar_arrive_expect_tx(&full_bar[s], (uint32_t)p.stage_bytes);
                 const int c = p.seg_c0[seg] + ch * kChunkK;
+#if defined(RAFT_TC_EXP) && (RAFT_TC_EXP & 6)        // mainloop experiments (tools/tc_exp.sh; run with RAFT_B200_PDL=0)
+                if (RAFT_TC_EXP & 2) {               // activations only
+                  mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(2 * kABytes));
+                  tma_load_5d(st, &p.a_map[seg], &full_bar[s], c, x0 + dx, y0 + dy, b, 0);
+                } else {                             // weights only
+                  mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(p.stage_bytes - 2 * kABytes));
+                  tma_load_4d(st + 2 * kABytes, &p.b_map, &full_bar[s], kc * kChunkK, n0, tap, 0);
+                }
+#else
+                if (it >= npre) mbar_arrive_expect_tx(&full_bar[s], (uint32_t)p.stage_bytes);
                 // two boxes per stage: [A_hi | A_lo] and [B_hi | B_lo] (TMA cost is per box, not per byte)
                 tma_load_5d(st, &p.a_map[seg], &full_bar[s], c, x0 + dx, y0 + dy, b, 0);
                 if (it >= npre) tma_load_4d(st + 2 * kABytes, &p.b_map, &full_bar[s], kc * kChunkK, n0, tap, 0);
+#endif
               }
             }
           }
@@ -556,6 +566,9 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarpsConv, 1) conv_tc_kernel(con
               const uint64_t a_lo = make_desc_sw128(sa + kABytes);
               const uint64_t b_hi = make_desc_sw128(sa + 2 * kABytes);
               const uint64_t b_lo = make_desc_sw128(sa + 2 * kABytes + b_bytes);
+#if defined(RAFT_TC_EXP) && (RAFT_TC_EXP & 1)        // experiment: no MMAs, only the commits
+              if (sa != 0xffffffffu) goto tc_exp_skip_mma;
+#endif
 #pragma unroll
               for (int k = 0; k < kChunkK / 16; ++k)   // +32 bytes per K=16 step == +2 in 16-byte units
                 umma_f16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (!first || k > 0) ? 1u : 0u);
@@ -563,6 +576,9 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarpsConv, 1) conv_tc_kernel(con
               for (int k = 0; k < kChunkK / 16; ++k) umma_f16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
 #pragma unroll
               for (int k = 0; k < kChunkK / 16; ++k) umma_f16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+#if defined(RAFT_TC_EXP) && (RAFT_TC_EXP & 1)
+            tc_exp_skip_mma:;
+#endif
             }
             umma_commit(&empty_bar[s]);                      // frees the smem slot once these MMAs retire
             if (done == gend - 1) umma_commit(&acc_full[buf]);   // group complete -> promotion warps

@@ -29,7 +29,8 @@ constexpr int kMegaEpiWarps = 16;
 // get ~2.7 (the SM's ingest limit, ~78 B/clk).  The stages of an item are therefore dealt round-robin to kMegaProducers
 // producer warps (warp 0 and the warps after the epilogue warps); each issues both boxes of its stages.
 constexpr int kMegaProducers = 2;
-constexpr int kMegaThreads = 64 + 32 * kMegaEpiWarps + 32 * (kMegaProducers - 1);
+constexpr int kMegaIssuer2Warp = 2 + kMegaEpiWarps + (kMegaProducers - 1);   // second MMA-issuing warp (see the issuer section)
+constexpr int kMegaThreads = 64 + 32 * kMegaEpiWarps + 32 * (kMegaProducers - 1) + 32;
 constexpr int kMegaMaxStages = 8;
 
 struct alignas(64) MegaLayer {
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
-  if (warp == 0 || warp >= 2 + kMegaEpiWarps) {
+  if (warp == 0 || (warp >= 2 + kMegaEpiWarps && warp < kMegaIssuer2Warp)) {
     // ===================== TMA producers =====================
     const int pid = warp == 0 ? 0 : warp - (2 + kMegaEpiWarps) + 1;       // this warp issues the stages seq % kMegaProducers == pid
     const bool claimer = rank == 0 && pid == 0;                            // ... and one of them claims the items
@@ -262,8 +263,15 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
         item = nxt;
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 || warp == kMegaIssuer2Warp) {
+    // ===================== MMA issuers =====================
+    // MEASURED (profiles/r02_mainloop_parts_experiment.log, r02_mma_issue_probe.log): a K chunk costs its MMA time PLUS ~550
+    // cycles -- the issuing thread's own barrier waits, descriptor arithmetic and commits between two batches of MMAs, during
+    // which the (shallow) MMA queue runs dry: 12 x max(40, N/2) + 550 cycles per chunk for every N, with or without the TMA
+    // boxes.  Two warps therefore issue alternate promotion GROUPS: group g goes to TMEM buffer g & 1, so warp 1 owns buffer
+    // 0 and warp kMegaIssuer2Warp buffer 1; their accumulation chains are independent (the promotion warps add the groups in
+    // order), each commit tracks its own thread's MMAs, and one warp's bookkeeping hides behind the other's MMAs.
+    const int iid = warp == 1 ? 0 : 1;
     uint32_t par = 0;
     int slot = 0, cur_nst = 0, cur_bytes = 0, gg = 0;
     for (int k = 0; rank == 0; ++k) {                    // (pair: the leader issues for both CTAs; the peer's warp 1 only
@@ -285,15 +293,19 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
       int done = 0;
       while (done < total) {
         const int buf = gg & 1;
-        mbar_wait(&acc_empty[buf], ((uint32_t)(gg >> 1) & 1u) ^ 1u);       // promotion warps drained this buffer
-        tc_fence_after();
+        const bool mine = buf == iid;                    // (both warps walk every group to keep slot and parity counts)
+        if (mine) {
+          mbar_wait(&acc_empty[buf], ((uint32_t)(gg >> 1) & 1u) ^ 1u);     // promotion warps drained this buffer
+          tc_fence_after();
+        }
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 256);
         const int gend = min(total, done + gsz);
         for (int first = 1; done < gend; ++done, first = 0) {
           const int s = slot;
           slot = slot + 1 == cur_nst ? 0 : slot + 1;
-          mbar_wait(&full_bar[s], (par >> s) & 1u);
+          if (mine) mbar_wait(&full_bar[s], (par >> s) & 1u);
           par ^= 1u << s;
+          if (!mine) continue;
           tc_fence_after();
           if (elect_one()) {
             const uint32_t sa = smem_u32(stages + (size_t)s * cur_bytes);

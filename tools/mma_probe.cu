@@ -7,7 +7,7 @@
 #include "../tf_raft_b200/csrc/tmap.cuh"
 using namespace raft;
 
-__global__ void __launch_bounds__(128, 1) mma_probe(int n, int reps, int issuers, int distinct, long long* out) {
+__global__ void __launch_bounds__(128, 1) mma_probe(int n, int reps, int issuers, int distinct, int commit_every, long long* out) {
 #if defined(__CUDA_ARCH__)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -18,6 +18,8 @@ __global__ void __launch_bounds__(128, 1) mma_probe(int n, int reps, int issuers
   if (threadIdx.x == 0) {
     mbar_init(&bar[0], 1);
     mbar_init(&bar[1], 1);
+    mbar_init(&bar[2], 1 << 20);   // sink of the in-loop commits (never completes a phase)
+    mbar_init(&bar[3], 1 << 20);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -41,6 +43,7 @@ __global__ void __launch_bounds__(128, 1) mma_probe(int n, int reps, int issuers
         // distinct: walk the four K=16 slices of a 64-channel chunk like the real mainloop; else the same operands every time
         const uint64_t off = distinct ? (uint64_t)(2 * (i & 3)) : 0;
         umma_f16(d, a0 + off, b0 + off, idesc, i > 0 ? 1u : 0u);
+        if (commit_every > 0 && (i + 1) % commit_every == 0) umma_commit(&bar[2 + warp]);   // like the mainloop: frees a stage
       }
       const long long t1 = clock64();
       umma_commit(&bar[warp]);
@@ -60,18 +63,19 @@ int main() {
   long long* out;
   cudaMalloc(&out, 64);
   cudaFuncSetAttribute(mma_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  printf("%5s %8s %9s %14s %16s %12s\n", "N", "issuers", "operands", "issue cyc/MMA", "complete cyc/MMA", "pipe N/2");
+  printf("%5s %8s %9s %8s %14s %16s %12s\n", "N", "issuers", "operands", "commit/", "issue cyc/MMA", "complete cyc/MMA", "pipe N/2");
   for (int n : {16, 32, 64, 128, 192, 256})
     for (int issuers : {1, 2})
-      for (int distinct : {0, 1}) {
-        const int reps = 4096;
-        mma_probe<<<1, 128, 100 * 1024>>>(n, reps, issuers, distinct, out);
-        mma_probe<<<1, 128, 100 * 1024>>>(n, reps, issuers, distinct, out);
+      for (int commit_every : {0, 12, 24})
+      for (int distinct : {1}) {
+        const int reps = 4080;
+        mma_probe<<<1, 128, 100 * 1024>>>(n, reps, issuers, distinct, commit_every, out);
+        mma_probe<<<1, 128, 100 * 1024>>>(n, reps, issuers, distinct, commit_every, out);
         if (cudaDeviceSynchronize() != cudaSuccess) { printf("failed: %s\n", cudaGetErrorString(cudaGetLastError())); return 1; }
         long long h[4];
         cudaMemcpy(h, out, 32, cudaMemcpyDeviceToHost);
         const long long issue = issuers == 2 ? (h[0] > h[2] ? h[0] : h[2]) : h[0], done = issuers == 2 ? (h[1] > h[3] ? h[1] : h[3]) : h[1];
-        printf("%5d %8d %9s %14.1f %16.1f %12d\n", n, issuers, distinct ? "4 slices" : "same", (double)issue / reps, (double)done / reps, n / 2);
+        printf("%5d %8d %9s %8d %14.1f %16.1f %12d\n", n, issuers, distinct ? "4 slices" : "same", commit_every, (double)issue / reps, (double)done / reps, n / 2);
       }
   return 0;
 }

@@ -116,7 +116,8 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
   uint64_t* acc_full = empty_bar + kMegaMaxStages;      // [2] issuer -> promotion warps
   uint64_t* acc_empty = acc_full + 2;                   // [2] promotion warps -> issuer
   uint64_t* q_bar = acc_empty + 2;                      // [kMegaQueue] producer -> consumers: item number published
-  int* item_q = reinterpret_cast<int*>(q_bar + kMegaQueue);
+  uint64_t* carve_bar = q_bar + kMegaQueue;             // [1] producer warps: all of them have seen the ring drained
+  int* item_q = reinterpret_cast<int*>(carve_bar + 1);
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(item_q + kMegaQueue);
 
   const int warp = threadIdx.x >> 5;
@@ -133,6 +134,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
       mbar_init(&acc_empty[i], kMegaEpiWarps * (kPair ? 2 : 1));   // every epilogue warp (of both CTAs) arrives
     }
     for (int i = 0; i < kMegaQueue; ++i) mbar_init(&q_bar[i], 1);
+    mbar_init(carve_bar, kMegaProducers);
     fence_mbar_init();
   }
   if (warp == 2 && lane < P.nlayers) {                   // descriptor fetches off the first stage of every layer
@@ -163,6 +165,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
       uint32_t par = 0, used = 0;          // per ring slot: parity of its use count, used since the last drain
       int slot = 0, cur_nst = 0, cur_bytes = 0;
       unsigned int seq = 0;                // stages since the start of the kernel (every producer counts all of them)
+      uint32_t carves = 0;                 // ring re-carves so far (parity of carve_bar)
       // Items are CLAIMED, not pre-assigned: a CTA that becomes free takes the lowest unclaimed item of the list (layer
       // order = priority order), so no CTA sits on a blocked item while a runnable one waits behind it in a fixed
       // per-CTA sequence.  Every dependency points to a lower item number, which some co-resident CTA has already claimed,
@@ -220,6 +223,14 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
         if (c.nstages != cur_nst || c.stage_bytes != cur_bytes) {
           for (int s = 0; s < kMegaMaxStages; ++s)
             if ((used >> s) & 1u) mbar_wait(&empty_bar[s], ((par >> s) & 1u) ^ 1u);   // MMAs of the slot's last use retired
+          // No producer may refill (and so advance the phase of) a slot barrier that another producer still has to check
+          // above: a parity wait that is overtaken by two phases never returns.  (Found on hardware: trap in the dependency
+          // wait of a consumer item once the two-issuer mainloop had made the producers fast enough to overtake each other.)
+          if (kMegaProducers > 1) {
+            mbar_arrive(carve_bar);
+            mbar_wait(carve_bar, carves & 1u);
+            ++carves;
+          }
           used = 0;
           slot = 0;
           cur_nst = c.nstages;

@@ -251,8 +251,12 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
               const int s = slot;
               slot = slot + 1 == cur_nst ? 0 : slot + 1;
               const bool mine = seq++ % kMegaProducers == (unsigned)pid;
-              if (mine) mbar_wait(&empty_bar[s], ((par >> s) & 1u) ^ 1u);
-              par ^= 1u << s;                                // (every producer tracks the use count of every slot)
+              // EVERY producer waits for EVERY use of every slot, in order: a parity wait only tells "the phase I expect has
+              // completed" apart from "not yet" if the waiter is never more than one phase away from the barrier -- skipping
+              // the other producer's uses would let a wait return one phase EARLY.  (The waits are on older uses; they cost
+              // the owner nothing.)
+              mbar_wait(&empty_bar[s], ((par >> s) & 1u) ^ 1u);
+              par ^= 1u << s;
               used |= 1u << s;
               if (!mine) continue;
               uint8_t* st = stages + (size_t)s * cur_bytes;
@@ -314,7 +318,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
         for (int first = 1; done < gend; ++done, first = 0) {
           const int s = slot;
           slot = slot + 1 == cur_nst ? 0 : slot + 1;
-          if (mine) mbar_wait(&full_bar[s], (par >> s) & 1u);
+          mbar_wait(&full_bar[s], (par >> s) & 1u);      // (both issuers wait for every stage: see the producers' note)
           par ^= 1u << s;
           if (!mine) continue;
           tc_fence_after();

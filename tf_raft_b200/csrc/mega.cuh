@@ -24,13 +24,7 @@ namespace raft {
 
 constexpr int kMegaMaxLayers = 14;
 constexpr int kMegaEpiWarps = 16;
-// TMA-issuing warps.  MEASURED (tools/tma_probe3.cu, profiles/r02_tma_probe_issuers.log): ONE issuing thread gets one box per
-// ~770-815 cycles whatever the box (16-64 KB, rank 2-5, 2-8 boxes in flight); two threads of different warps get two, three
-// get ~2.7 (the SM's ingest limit, ~78 B/clk).  The stages of an item are therefore dealt round-robin to kMegaProducers
-// producer warps (warp 0 and the warps after the epilogue warps); each issues both boxes of its stages.
-constexpr int kMegaProducers = 2;
-constexpr int kMegaIssuer2Warp = 2 + kMegaEpiWarps + (kMegaProducers - 1);   // second MMA-issuing warp (see the issuer section)
-constexpr int kMegaThreads = 64 + 32 * kMegaEpiWarps + 32 * (kMegaProducers - 1) + 32;
+constexpr int kMegaThreads = 64 + 32 * kMegaEpiWarps;
 constexpr int kMegaMaxStages = 8;
 
 struct alignas(64) MegaLayer {
@@ -116,8 +110,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
   uint64_t* acc_full = empty_bar + kMegaMaxStages;      // [2] issuer -> promotion warps
   uint64_t* acc_empty = acc_full + 2;                   // [2] promotion warps -> issuer
   uint64_t* q_bar = acc_empty + 2;                      // [kMegaQueue] producer -> consumers: item number published
-  uint64_t* carve_bar = q_bar + kMegaQueue;             // [1] producer warps: all of them have seen the ring drained
-  int* item_q = reinterpret_cast<int*>(carve_bar + 1);
+  int* item_q = reinterpret_cast<int*>(q_bar + kMegaQueue);
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(item_q + kMegaQueue);
 
   const int warp = threadIdx.x >> 5;
@@ -134,7 +127,6 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
       mbar_init(&acc_empty[i], kMegaEpiWarps * (kPair ? 2 : 1));   // every epilogue warp (of both CTAs) arrives
     }
     for (int i = 0; i < kMegaQueue; ++i) mbar_init(&q_bar[i], 1);
-    mbar_init(carve_bar, kMegaProducers);
     fence_mbar_init();
   }
   if (warp == 2 && lane < P.nlayers) {                   // descriptor fetches off the first stage of every layer
@@ -157,23 +149,24 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
-  if (warp == 0 || (warp >= 2 + kMegaEpiWarps && warp < kMegaIssuer2Warp)) {
-    // ===================== TMA producers =====================
-    const int pid = warp == 0 ? 0 : warp - (2 + kMegaEpiWarps) + 1;       // this warp issues the stages seq % kMegaProducers == pid
-    const bool claimer = rank == 0 && pid == 0;                            // ... and one of them claims the items
+  if (warp == 0) {
+    // ===================== TMA producer =====================
     if (elect_one()) {
       uint32_t par = 0, used = 0;          // per ring slot: parity of its use count, used since the last drain
       int slot = 0, cur_nst = 0, cur_bytes = 0;
-      unsigned int seq = 0;                // stages since the start of the kernel (every producer counts all of them)
-      uint32_t carves = 0;                 // ring re-carves so far (parity of carve_bar)
+      // (One producer thread and one issuer thread.  Round-robin producer warps, a separate weight-producer warp and two
+      //  MMA-issuing warps on alternate promotion groups were all built, validated bit-identical and measured within +-2 % of
+      //  this form -- profiles/README.md "what bounds the mainloop": shared-memory bandwidth, not issue.  Lesson kept from the
+      //  multi-warp forms: a thread that waits on the parity of a barrier must wait for EVERY phase of it, in order; skipping
+      //  the phases that belong to another warp lets a parity wait return one phase early, or never.)
       // Items are CLAIMED, not pre-assigned: a CTA that becomes free takes the lowest unclaimed item of the list (layer
       // order = priority order), so no CTA sits on a blocked item while a runnable one waits behind it in a fixed
       // per-CTA sequence.  Every dependency points to a lower item number, which some co-resident CTA has already claimed,
       // so the wait graph stays acyclic.  The claimed number is handed to the other roles through item_q / q_bar.
-      int item = claimer ? (int)atomicAdd(P.next_item, 1u) : 0;
+      int item = rank == 0 ? (int)atomicAdd(P.next_item, 1u) : 0;
       for (int k = 0;; ++k) {
         const int qs = k & (kMegaQueue - 1);
-        if (claimer) {
+        if (rank == 0) {
           const int pub = item < P.nitems ? item : -1;
           item_q[qs] = pub;
           mbar_arrive(&q_bar[qs]);                       // (release: the slot's item number is visible to the waiters)
@@ -188,7 +181,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
         }
         if (item >= P.nitems) break;
 #ifdef RAFT_MEGA_TRACE
-        long long* dbg = (P.dbg && pid == 0 && k < kMegaDbgItems) ? P.dbg + ((size_t)blockIdx.x * kMegaDbgItems + k) * 8 : nullptr;
+        long long* dbg = (P.dbg && k < kMegaDbgItems) ? P.dbg + ((size_t)blockIdx.x * kMegaDbgItems + k) * 8 : nullptr;
         if (dbg) { dbg[0] = item + 1; dbg[1] = global_ns(); }
 #endif
         int nxt = P.nitems;
@@ -223,14 +216,6 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
         if (c.nstages != cur_nst || c.stage_bytes != cur_bytes) {
           for (int s = 0; s < kMegaMaxStages; ++s)
             if ((used >> s) & 1u) mbar_wait(&empty_bar[s], ((par >> s) & 1u) ^ 1u);   // MMAs of the slot's last use retired
-          // No producer may refill (and so advance the phase of) a slot barrier that another producer still has to check
-          // above: a parity wait that is overtaken by two phases never returns.  (Found on hardware: trap in the dependency
-          // wait of a consumer item once the two-issuer mainloop had made the producers fast enough to overtake each other.)
-          if (kMegaProducers > 1) {
-            mbar_arrive(carve_bar);
-            mbar_wait(carve_bar, carves & 1u);
-            ++carves;
-          }
           used = 0;
           slot = 0;
           cur_nst = c.nstages;
@@ -247,18 +232,12 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
             for (int ch = 0; ch < c.seg_chunks[seg]; ++ch, ++kc) {
               // claim the next item while the last stage of this one is still to be loaded: late enough that the CTA is
               // about to be free, early enough that the atomic's round trip hides behind the slot wait below
-              if (--left == 0 && claimer) nxt = (int)atomicAdd(P.next_item, 1u);
+              if (--left == 0 && rank == 0) nxt = (int)atomicAdd(P.next_item, 1u);
               const int s = slot;
               slot = slot + 1 == cur_nst ? 0 : slot + 1;
-              const bool mine = seq++ % kMegaProducers == (unsigned)pid;
-              // EVERY producer waits for EVERY use of every slot, in order: a parity wait only tells "the phase I expect has
-              // completed" apart from "not yet" if the waiter is never more than one phase away from the barrier -- skipping
-              // the other producer's uses would let a wait return one phase EARLY.  (The waits are on older uses; they cost
-              // the owner nothing.)
               mbar_wait(&empty_bar[s], ((par >> s) & 1u) ^ 1u);
               par ^= 1u << s;
               used |= 1u << s;
-              if (!mine) continue;
               uint8_t* st = stages + (size_t)s * cur_bytes;
               if constexpr (kPair) {
                 // both CTAs' boxes complete on the LEADER's barrier, which expects the bytes of both stages
@@ -278,15 +257,8 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
         item = nxt;
       }
     }
-  } else if (warp == 1 || warp == kMegaIssuer2Warp) {
-    // ===================== MMA issuers =====================
-    // MEASURED (profiles/r02_mainloop_parts_experiment.log, r02_mma_issue_probe.log): a K chunk costs its MMA time PLUS ~550
-    // cycles -- the issuing thread's own barrier waits, descriptor arithmetic and commits between two batches of MMAs, during
-    // which the (shallow) MMA queue runs dry: 12 x max(40, N/2) + 550 cycles per chunk for every N, with or without the TMA
-    // boxes.  Two warps therefore issue alternate promotion GROUPS: group g goes to TMEM buffer g & 1, so warp 1 owns buffer
-    // 0 and warp kMegaIssuer2Warp buffer 1; their accumulation chains are independent (the promotion warps add the groups in
-    // order), each commit tracks its own thread's MMAs, and one warp's bookkeeping hides behind the other's MMAs.
-    const int iid = warp == 1 ? 0 : 1;
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
     uint32_t par = 0;
     int slot = 0, cur_nst = 0, cur_bytes = 0, gg = 0;
     for (int k = 0; rank == 0; ++k) {                    // (pair: the leader issues for both CTAs; the peer's warp 1 only
@@ -308,19 +280,15 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
       int done = 0;
       while (done < total) {
         const int buf = gg & 1;
-        const bool mine = buf == iid;                    // (both warps walk every group to keep slot and parity counts)
-        if (mine) {
-          mbar_wait(&acc_empty[buf], ((uint32_t)(gg >> 1) & 1u) ^ 1u);     // promotion warps drained this buffer
-          tc_fence_after();
-        }
+        mbar_wait(&acc_empty[buf], ((uint32_t)(gg >> 1) & 1u) ^ 1u);       // promotion warps drained this buffer
+        tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 256);
         const int gend = min(total, done + gsz);
         for (int first = 1; done < gend; ++done, first = 0) {
           const int s = slot;
           slot = slot + 1 == cur_nst ? 0 : slot + 1;
-          mbar_wait(&full_bar[s], (par >> s) & 1u);      // (both issuers wait for every stage: see the producers' note)
+          mbar_wait(&full_bar[s], (par >> s) & 1u);
           par ^= 1u << s;
-          if (!mine) continue;
           tc_fence_after();
           if (elect_one()) {
             const uint32_t sa = smem_u32(stages + (size_t)s * cur_bytes);

@@ -324,7 +324,7 @@ def run_ours(args, cfg):
                 cb.precision, _lib.stream()), 'corr_pyramid_build')
         t_corr = ev_time(build_corr)
         # the loop exactly as the timed step runs it (last prediction only), with the library's per-kernel events armed:
-        # lookup = the fp16 hi/lo-plane variant the loop uses, update = flow_im2col + the update-block kernel(s)
+        # lookup = the fp16 hi/lo-plane variant the loop uses (it also writes convf1's im2col planes), update = the update-block kernel(s)
         preds = [None] * (ITERS - 1) + [torch.empty((B, H, W, 2), device=device)]
         L = _lib.lib()
         reps, t_lookup, t_update = 3, 0.0, 0.0
@@ -403,7 +403,7 @@ def run_ours(args, cfg):
             'clocks': clocks,
             'roofline': {'bound': 'tensor',
                          'kernel': 'update_mega_kernel (all tensor-core layers of one update-block application; one launch per '
-                                   'iteration, timed together with the 11 us flow_im2col gather that precedes it)',
+                                   'iteration)',
                          'achieved': ach_tflops, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
                          'frac': ach_tflops / peaks['bf16_tflops'],
                          'traffic': mega_traffic,

@@ -376,3 +376,41 @@ def test_predict_stream_equals_synchronous_predict_step(T):
         assert len(got) == len(want)
         for k, (g, w) in enumerate(zip(got, want)):
             assert torch.equal(g, w), f'pair {k}, reuse_host_buffers={reuse}'
+
+
+# ---------------------------------------------------------------- the three forms of the update block's tensor-core layers
+_FORM_SCRIPT = r'''
+import hashlib, os, sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], 'tests'))
+import torch
+import cases
+from oracle import weights
+import tf_raft_b200 as T
+blk = T.BasicUpdateBlock(precision='f16x2')
+blk.load_params(weights.init_params('raft', 1234), 'update_block.')
+net, inp, corr, flow = [torch.from_numpy(a).cuda() for a in cases.update_inputs('raft', 4, 56, 64)]
+out = blk([net, inp, corr, flow])
+torch.cuda.synchronize()
+h = hashlib.sha256()
+for t in out:
+    h.update(t.cpu().numpy().tobytes())
+print('HASH', h.hexdigest())
+'''
+
+
+def test_update_block_forms_are_bit_identical(T):
+    """update_mega_kernel<true> (CTA pairs, tcgen05 cta_group::2: the default at an even tile count), update_mega_kernel<false>
+    (RAFT_B200_PAIR=0) and one launch per layer (RAFT_B200_MEGA=0) run the same accumulation chains in the same order: their
+    outputs (net, mask, delta_flow) at batch 4, 56x64 must be identical byte for byte.  (The switches are read once per
+    process, hence the subprocesses.)"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), '..'))
+    hashes = {}
+    for name, env in (('pair', {}), ('single', {'RAFT_B200_PAIR': '0'}), ('per_layer', {'RAFT_B200_MEGA': '0'})):
+        res = subprocess.run([sys.executable, '-c', _FORM_SCRIPT, root], env={**os.environ, **env}, capture_output=True, text=True,
+                             timeout=300)
+        assert res.returncode == 0, f'{name}: {res.stderr[-2000:]}'
+        hashes[name] = [l for l in res.stdout.splitlines() if l.startswith('HASH')][-1]
+    assert hashes['pair'] == hashes['single'] == hashes['per_layer'], hashes

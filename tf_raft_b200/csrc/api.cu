@@ -258,8 +258,10 @@ static int flow_branch_basic_tc(const UpdateCtx& c, int part) {
   TcConvParams p;
   if (part == 0) {  // convf1 7x7 2->128 + relu: K = 98 -> gather the window into 128-channel planes, run as a 1x1 GEMM
     const size_t npix = (size_t)c.B * c.h * c.w;
-    flow_im2col_kernel<<<grid_for(npix * 128), 256, 0, c.stream>>>(W.flow, c.B, c.h, c.w, W.fim_hi, W.fim_lo);
-    RAFT_COUNT_LAUNCH();
+    if (!c.fim_ready) {              // (the iteration loop's lookup kernel has already produced the planes)
+      flow_im2col_kernel<<<grid_for(npix * 128), 256, 0, c.stream>>>(W.flow, c.B, c.h, c.w, W.fim_hi, W.fim_lo);
+      RAFT_COUNT_LAUNCH();
+    }
     tc_params_init(p, EPI_LINEAR, ACT_RELU, 128);
     p.out_hi = W.flo1_hi; p.out_lo = W.flo1_lo; p.h_stride = d.s_flo1;
     TcSeg s[1] = {{W.fim_hi, W.fim_lo, 128, 0, 2}};
@@ -330,8 +332,10 @@ static int update_core_tc(const UpdateCtx& c, float* h, float* delta, float* mas
     }
     {  // convf1 7x7 2->64 + relu via im2col + 1x1 GEMM
       const size_t npix = (size_t)c.B * c.h * c.w;
-      flow_im2col_kernel<<<grid_for(npix * 128), 256, 0, c.stream>>>(W.flow, c.B, c.h, c.w, W.fim_hi, W.fim_lo);
-      RAFT_COUNT_LAUNCH();
+      if (!c.fim_ready) {
+        flow_im2col_kernel<<<grid_for(npix * 128), 256, 0, c.stream>>>(W.flow, c.B, c.h, c.w, W.fim_hi, W.fim_lo);
+        RAFT_COUNT_LAUNCH();
+      }
       tc_params_init(p, EPI_LINEAR, ACT_RELU, 64);
       p.out_hi = W.flo1_hi; p.out_lo = W.flo1_lo; p.h_stride = d.s_flo1;
       TcSeg s[1] = {{W.fim_hi, W.fim_lo, 128, 0, 2}};
@@ -403,6 +407,7 @@ static int make_ctx(UpdateCtx& c, int variant, const void* prepared, int B, int 
   if (c.W.total > ws_bytes) return RAFT_ERR_WORKSPACE;
   c.stream = reinterpret_cast<cudaStream_t>(stream);
   c.plan = nullptr;
+  c.fim_ready = false;
   return 0;
 }
 
@@ -456,9 +461,11 @@ static int update_once(int variant, const void* prepared, const float* net, cons
   return update_core_fp32(c, net_out, delta, mask);
 }
 
+// im_flow != null (iteration loop, tensor-core path): the convf1 im2col planes im_hi / im_lo are produced too -- by the
+// window kernel itself when it runs, else by flow_im2col_kernel.
 static int lookup_launch(const float* const pyr[], const float* coords, int B, int h, int w, int levels, int radius,
                          float* out, int out_stride, __half* out_hi, __half* out_lo, int h_stride, int h_pad,
-                         cudaStream_t st) {
+                         cudaStream_t st, const float* im_flow = nullptr, __half* im_hi = nullptr, __half* im_lo = nullptr) {
   LookupParams p;
   memset(&p, 0, sizeof(p));
   int lh = h, lw = w;
@@ -474,10 +481,16 @@ static int lookup_launch(const float* const pyr[], const float* coords, int B, i
   p.out = out; p.out_stride = out_stride;
   p.out_hi = out_hi; p.out_lo = out_lo; p.h_stride = h_stride; p.h_pad = h_pad;
   p.nq = B * h * w; p.levels = levels; p.radius = radius;
+  p.im_flow = im_flow; p.im_hi = im_hi; p.im_lo = im_lo; p.im_B = B; p.im_h = h; p.im_w = w;
   const size_t nwork = (size_t)p.nq * levels;
   static const int gather = [] { const char* e = getenv("RAFT_B200_LOOKUP_GATHER"); return e ? atoi(e) : 0; }();   // A/B: force the generic kernel
-  if (gather || !lookup_win_launch(p, levels, radius, st))         // window kernel for the model's (radius, levels); else generic
+  if (gather || !lookup_win_launch(p, levels, radius, st)) {       // window kernel for the model's (radius, levels); else generic
     corr_lookup_kernel<<<grid_for(nwork * 32, 256, kNumSMs * 32), 256, 0, st>>>(p);
+    if (im_flow) {
+      flow_im2col_kernel<<<grid_for((size_t)p.nq * 128), 256, 0, st>>>(im_flow, B, h, w, im_hi, im_lo);
+      RAFT_COUNT_LAUNCH();
+    }
+  }
   RAFT_COUNT_LAUNCH();
   return raft_launch_status();
 }
@@ -854,9 +867,11 @@ int raft_b200_forward_loop(int variant, const void* prepared, const float* const
     if (precision == RAFT_PREC_F16X2) {
       if (prof) RAFT_CUDA_TRY(cudaEventRecord(g_prof.ev[i][0], c.stream));
       RAFT_TRY(lookup_launch(pyr, coords1, B, h, w, levels, radius, nullptr, 0, W.corr_hi, W.corr_lo, d.s_corr, d.s_corr,
-                             c.stream));                                                            // model.py:95
+                             c.stream, W.flow, W.fim_hi, W.fim_lo));                                // model.py:95 (+ convf1's im2col)
       if (prof) RAFT_CUDA_TRY(cudaEventRecord(g_prof.ev[i][1], c.stream));
+      c.fim_ready = true;
       RAFT_TRY(update_block_tc(c, net, W.delta, mask, coords1));                                    // :99, :102 (fused advance)
+      c.fim_ready = false;
       if (prof) RAFT_CUDA_TRY(cudaEventRecord(g_prof.ev[i][2], c.stream));
     } else {
       RAFT_TRY(lookup_launch(pyr, coords1, B, h, w, levels, radius, W.corr, d.corr_ch, nullptr, nullptr, 0, 0, c.stream));

@@ -110,6 +110,9 @@ struct LookupParams {
   __half* out_hi; __half* out_lo; int h_stride, h_pad;
   int nq;      // B*h*w
   int levels, radius;
+  // Optional rider of the window kernel (iteration loop): the 7x7 im2col of the current flow for convf1 (update.py:92) --
+  // independent of the lookup, tiny, and one launch less per iteration when it shares the lookup's grid.
+  const float* im_flow; __half* im_hi; __half* im_lo; int im_B, im_h, im_w;
 };
 
 __global__ void __launch_bounds__(256) corr_lookup_kernel(const LookupParams p) {
@@ -689,6 +692,33 @@ __global__ void stem_im2col_kernel(const float* __restrict__ img, int N, int H, 
       }
 #pragma unroll
       for (int e = 0; e < 4; ++e) split_f16x2(v[2 * e], v[2 * e + 1], ph[e], pl[e]);
+    }
+    reinterpret_cast<uint4*>(hi)[i] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+    reinterpret_cast<uint4*>(lo)[i] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+  }
+}
+
+// The same gather, 8 channels (4 taps x 2 flow components) per thread and 16-byte stores, as a grid-stride device routine
+// (called by every thread of corr_lookup_win_kernel after its lookups when the loop asks for it; values identical to
+// flow_im2col_kernel).
+__device__ __forceinline__ void flow_im2col_rider(const float* __restrict__ flow, int B, int h, int w, __half* __restrict__ hi,
+                                                  __half* __restrict__ lo, size_t tid, size_t nthreads) {
+  const size_t total = (size_t)B * h * w * 16;
+  for (size_t i = tid; i < total; i += nthreads) {
+    const int g = (int)(i & 15);
+    const size_t px = i >> 4;
+    const int x = (int)(px % w), y = (int)((px / w) % h);
+    uint32_t ph[4], pl[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int tap = 4 * g + e;
+      float2 v = make_float2(0.f, 0.f);
+      if (tap < 49) {
+        const int yy = y + tap / 7 - 3, xx = x + tap % 7 - 3;
+        if (yy >= 0 && yy < h && xx >= 0 && xx < w)
+          v = __ldg(reinterpret_cast<const float2*>(flow) + (ptrdiff_t)px + (ptrdiff_t)(yy - y) * w + (xx - x));
+      }
+      split_f16x2(v.x, v.y, ph[e], pl[e]);
     }
     reinterpret_cast<uint4*>(hi)[i] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
     reinterpret_cast<uint4*>(lo)[i] = make_uint4(pl[0], pl[1], pl[2], pl[3]);

@@ -187,6 +187,9 @@ __global__ void __launch_bounds__(256, 4) corr_lookup_win_kernel(const LookupPar
     }
     o_off += o_step;
   }
+  if (p.im_flow)
+    flow_im2col_rider(p.im_flow, p.im_B, p.im_h, p.im_w, p.im_hi, p.im_lo, (size_t)blockIdx.x * blockDim.x + threadIdx.x,
+                      (size_t)gridDim.x * blockDim.x);
 }
 
 // Launch for (radius, levels) in {(4,4), (3,4)}; returns false when the configuration has no window instantiation.

@@ -206,6 +206,7 @@ struct UpdateCtx {
   PreparedLayout PL;
   Workspace W;
   cudaStream_t stream;
+  bool fim_ready;      // the convf1 im2col planes of the current flow already exist (written by the loop's lookup kernel)
   MegaPlan* plan;      // non-null: tensor-core layers are collected here and run as ONE update_mega_kernel launch
 };
 

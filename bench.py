@@ -348,7 +348,10 @@ def run_ours(args, cfg):
         ach_tflops = flops_per_launch / max(t_update, 1e-9) / 1e12
         corr_bytes_pair = 4 * sum(PX * ((H // 8) >> l) * ((W // 8) >> l) for l in range(4)) + 8 * PX * 256
         lookup_bytes = B * PX * 2904
-        corr_bytes = B * corr_bytes_pair + ITERS * lookup_bytes
+        # in the loop the lookup launch also writes the im2col planes of the current flow for convf1 (2 planes x 128 channels x
+        # 2 bytes per query, + the 8-byte flow it reads): part of that launch's algorithmic traffic, listed separately
+        rider_bytes = B * PX * (2 * 128 * 2 + 8)
+        corr_bytes = B * corr_bytes_pair + ITERS * (lookup_bytes + rider_bytes)
         ach_gbs = corr_bytes / (t_corr + ITERS * t_lookup) / 1e9
         corr_flops_3pass = 3 * B * 2.0 * 256 * sum(PX * ((H // 8) >> l) * ((W // 8) >> l) for l in range(4))
 
@@ -425,6 +428,7 @@ def run_ours(args, cfg):
                                      'traffic': {'lookup': traffic.get('corr_lookup_win_kernel'),
                                                  'correlation': traffic.get('corr_tc_kernel'),
                                                  'lookup_algorithmic_bytes': lookup_bytes,
+                                                 'lookup_launch_im2col_rider_bytes': rider_bytes,
                                                  'correlation_algorithmic_bytes': B * corr_bytes_pair},
                                      'ms': {'pyramid_build': t_corr * 1e3, 'lookup': t_lookup * 1e3},
                                      'pyramid_build_alone': {
@@ -432,7 +436,7 @@ def run_ours(args, cfg):
                                          'tensor_frac_3pass': corr_flops_3pass / t_corr / 1e12 / peaks['bf16_tflops_burst'],
                                          'note': 'the fp32-grade correlation needs 3 fp16 passes, which makes the tensor pipe '
                                                  '(burst cuBLAS peak) its tighter bound; both fractions given'},
-                                     'lookup_alone_hbm_frac': lookup_bytes / t_lookup / 1e9 / peaks['hbm_gbs'],
+                                     'lookup_alone_hbm_frac': (lookup_bytes + rider_bytes) / t_lookup / 1e9 / peaks['hbm_gbs'],
                                      'peak_source': peaks['source']},
             'cpu_baseline': {'value': cpu_pps, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port',
                              'sample': f'1 pair ({H}x{W}, {ITERS} iterations) x 3 steps after 1 warm-up, '

@@ -105,6 +105,14 @@ def test_key_mapping_covers_the_reference_parameter_tree(tmp_path, variant, with
     assert set(got) == set(params)
     for k, v in params.items():
         assert np.array_equal(got[k], np.asarray(v)), k
+    # expect=: one error that names what is missing / unexpected / mis-shaped, instead of a KeyError later
+    assert set(ck.load_tf_checkpoint(prefix, expect=params)) == set(params)
+    broken = dict(params)
+    gone = broken.pop('fnet.conv1.bias')
+    broken['fnet.conv1.kernel'] = np.zeros((7, 7, 3, 1), dtype=np.float32)
+    broken['cnet.not_in_the_checkpoint'] = gone
+    with pytest.raises(ValueError, match='missing.*cnet.not_in_the_checkpoint.*unexpected.*fnet.conv1.bias.*shapes.*fnet.conv1.kernel'):
+        ck.load_tf_checkpoint(prefix, expect=broken)
 
 
 def test_key_mapping_examples():

@@ -315,8 +315,12 @@ def tf_key_to_param(key):
     return '.'.join(out)
 
 
-def load_tf_checkpoint(prefix, verify=False):
-    """Checkpoint -> `{param name: ndarray}` for `RAFT.load_params` / `SmallRAFT.load_params`."""
+def load_tf_checkpoint(prefix, verify=False, expect=None):
+    """Checkpoint -> `{param name: ndarray}` for `RAFT.load_params` / `SmallRAFT.load_params`.
+
+    `expect` = the model's `state_dict()` (name -> array-like): the mapped checkpoint must then cover exactly those names
+    with those shapes; anything missing, unexpected or mis-shaped is reported in ONE error instead of surfacing later as a
+    `KeyError` for the first missing name."""
     params = {}
     for key, value in read_tf_checkpoint(prefix, verify).items():
         name = tf_key_to_param(key)
@@ -324,4 +328,13 @@ def load_tf_checkpoint(prefix, verify=False):
             params[name] = value
     if not params:
         raise ValueError(f'{prefix}: no fnet/ cnet/ update_block/ variables found')
+    if expect is not None:
+        want = {k: tuple(np.shape(v)) for k, v in dict(expect).items()}
+        missing = sorted(set(want) - set(params))
+        extra = sorted(set(params) - set(want))
+        shapes = sorted(f'{k}: checkpoint {tuple(params[k].shape)} vs model {want[k]}' for k in set(want) & set(params)
+                        if tuple(params[k].shape) != want[k])
+        if missing or extra or shapes:
+            raise ValueError(f'{prefix}: does not match the model -- missing {missing[:8]}{"..." if len(missing) > 8 else ""}, '
+                             f'unexpected {extra[:8]}{"..." if len(extra) > 8 else ""}, shapes {shapes[:8]}')
     return params

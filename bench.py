@@ -42,6 +42,11 @@ N_ROTATE = 12            # distinct input batches cycled through: 12 x 2 x 11 MB
 
 # Algorithmic work of BasicUpdateBlock per feature-grid pixel (update.py:128-153)
 UPDATE_MAC_PER_PX = 3_118_336
+# Tensor-core layers of one BasicUpdateBlock application without the mask head (update.py:143-153): (output columns N of the
+# tile, 64-channel K chunks incl. taps) -- convc1, convf1, convc2, convf2, conv, z|r x2, q x2, flow_head.conv1, flow_head.conv2
+# (N = 32: the CTA pair's minimum).  Used for the shared-memory traffic of update_mega_kernel.
+UPDATE_LAYERS_N_CHUNKS = ((256, 6), (128, 2), (192, 36), (64, 18), (128, 36), (256, 30), (256, 30), (128, 30), (128, 30),
+                          (256, 18), (32, 36))
 MASK_MAC_PER_PX = 294_912 + 147_456               # mask[0] 3x3 128->256 + mask[2] 1x1 256->576 (update.py:137-141): only
                                                   # executed on iterations whose prediction is upsampled
 
@@ -421,7 +426,17 @@ def run_ours(args, cfg):
                                  'mask head on the one upsampled iteration, averaged over the launches) / CUDA-event time per '
                                  'launch measured inside raft_b200_forward_loop; the kernel executes 3 fp16 MMA passes per '
                                  'FLOP, so the tensor pipe is 3x busier than `frac`',
-                         'executed_frac': 3 * ach_tflops / peaks['bf16_tflops']},
+                         'executed_frac': 3 * ach_tflops / peaks['bf16_tflops'],
+                         # what the mainloop is measured to sit on (profiles/README.md): per 64-channel chunk a CTA of a pair
+                         # receives 32 KB of activations + N/2 weight rows by TMA and its twelve MMAs read 12 x (4 KB + N x 32 B)
+                         'shared_memory': (lambda by, pk: {
+                             'bytes_per_launch': by, 'achieved_TBps': by / max(t_update, 1e-9) / 1e12, 'peak_TBps': pk / 1e12,
+                             'frac': by / max(t_update, 1e-9) / pk,
+                             'note': 'TMA writes + tcgen05 operand reads of shared memory per launch (mask head excluded) against '
+                                     '148 SMs x 128 B/clk at the sampled SM clock; a layer has 112 tiles for 148 SMs and the 9 '
+                                     'chain layers run one after the other, so 0.76 of this peak is the structural ceiling'})(
+                             B * PX / 128 * sum(c * (32768 + (n // 2) * 256 + 12 * (4096 + n * 32)) for n, c in UPDATE_LAYERS_N_CHUNKS),
+                             148 * 128 * 1e6 * float((clocks or {}).get('sm_mhz') or 1965))},
             'roofline_corr_lookup': {'bound': 'hbm', 'kernel': f'correlation pyramid build + {ITERS} lookups',
                                      'achieved': ach_gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                                      'frac': ach_gbs / peaks['hbm_gbs'],

@@ -433,8 +433,8 @@ def run_ours(args, cfg):
                              'bytes_per_launch': by, 'achieved_TBps': by / max(t_update, 1e-9) / 1e12, 'peak_TBps': pk / 1e12,
                              'frac': by / max(t_update, 1e-9) / pk,
                              'note': 'TMA writes + tcgen05 operand reads of shared memory per launch (mask head excluded) against '
-                                     '148 SMs x 128 B/clk at the sampled SM clock; a layer has 112 tiles for 148 SMs and the 9 '
-                                     'chain layers run one after the other, so 0.76 of this peak is the structural ceiling'})(
+                                     f'148 SMs x 128 B/clk at the sampled SM clock; a layer has {B * PX // 128} tiles for 148 SMs and '
+                                     'the 9 chain layers run one after the other (at 112 tiles: 0.76 of this peak at most)'})(
                              B * PX / 128 * sum(c * (32768 + (n // 2) * 256 + 12 * (4096 + n * 32)) for n, c in UPDATE_LAYERS_N_CHUNKS),
                              148 * 128 * 1e6 * float((clocks or {}).get('sm_mhz') or 1965))},
             'roofline_corr_lookup': {'bound': 'hbm', 'kernel': f'correlation pyramid build + {ITERS} lookups',

@@ -2,7 +2,9 @@
 claim / dependencies satisfied / ring ready / all loads issued (producer) and first group ready / last group drained /
 epilogue done (epilogue warp 2).  Prints per-layer statistics and the critical chain of one pixel tile.
 
-usage: python tools/timeline_mega.py            (RAFT_B200_PAIR=0 for the single-CTA form)
+usage: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -shared -Xcompiler -fPIC -DRAFT_MEGA_TRACE \
+           tf_raft_b200/csrc/api.cu -o tools/epi_exp/mega_trace.so          (the stamps are compiled out of the product build)
+       RAFT_B200_LIB=$PWD/tools/epi_exp/mega_trace.so python tools/timeline_mega.py     (RAFT_B200_PAIR=0: single-CTA form)
 """
 import os, sys
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), '..'))

@@ -278,6 +278,71 @@ __device__ __forceinline__ void umma2_commit(uint64_t* bar) {
                "h"((uint16_t)3)
                : "memory");
 }
+// --- one 64-channel chunk of the three-pass product hi*hi + hi*lo + lo*hi ------------------------------------------------
+// The mainloops are bound by shared-memory bandwidth and every MMA re-reads its A slice (4 KB) from shared
+// memory.  The tensor core has an A COLLECTOR buffer: `.collector::a::fill` keeps the slice, `.collector::a::lastuse` on the
+// next MMA reuses it without a shared-memory read (SASS: UTCHMMA ... .A_KEEP / .A_REUSE; measured, tools/mma_probe.cu: an
+// N = 64 MMA stream goes from 48 to 40 cycles per MMA, its issue floor).  So per K=16 slice hi*hi (fill) is followed directly
+// by hi*lo (lastuse), and the four lo*hi slices close the chunk: 8 A reads per chunk instead of 12.  All tensor-core kernels
+// issue their chunks through this routine, so their accumulation order -- and their results -- stay identical to each other.
+// RAFT_A_COLLECTOR=0 at compile time restores the round-1 order (hi*hi x4, lo*hi x4, hi*lo x4; A/B builds).
+#ifndef RAFT_A_COLLECTOR
+#define RAFT_A_COLLECTOR 1
+#endif
+#define RAFT_UMMA_ASM(GROUP, COLL)                                                                                    \
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"                                                            \
+               "tcgen05.mma.cta_group::" GROUP ".kind::f16" COLL " [%0], %1, %2, %3, p;\n}\n" ::"r"(d), "l"(a), "l"(b), \
+               "r"(idesc), "r"(acc)                                                                                   \
+               : "memory")
+template <bool kPair, int kColl>   // kColl: 0 plain, 1 fill, 2 lastuse
+__device__ __forceinline__ void umma_f16_c(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  if constexpr (kPair) {
+    if constexpr (kColl == 1) RAFT_UMMA_ASM("2", ".collector::a::fill");
+    else if constexpr (kColl == 2) RAFT_UMMA_ASM("2", ".collector::a::lastuse");
+    else RAFT_UMMA_ASM("2", "");
+  } else {
+    if constexpr (kColl == 1) RAFT_UMMA_ASM("1", ".collector::a::fill");
+    else if constexpr (kColl == 2) RAFT_UMMA_ASM("1", ".collector::a::lastuse");
+    else RAFT_UMMA_ASM("1", "");
+  }
+}
+// a_hi / a_lo / b_hi / b_lo: descriptors of the chunk's first K=16 slice (+2 per slice); first: the chunk opens an accumulation
+template <bool kPair>
+__device__ __forceinline__ void umma_chunk3(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo, uint32_t idesc,
+                                            bool first) {
+#if RAFT_A_COLLECTOR == 1
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    umma_f16_c<kPair, 1>(d, a_hi + 2 * k, b_hi + 2 * k, idesc, (!first || k > 0) ? 1u : 0u);
+    umma_f16_c<kPair, 2>(d, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) umma_f16_c<kPair, 0>(d, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+#elif RAFT_A_COLLECTOR == 2      // (other pairings of the same products, kept for the parity study of the benchmark seed)
+#pragma unroll
+  for (int k = 0; k < 4; ++k) umma_f16_c<kPair, 0>(d, a_lo + 2 * k, b_hi + 2 * k, idesc, (!first || k > 0) ? 1u : 0u);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    umma_f16_c<kPair, 1>(d, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
+    umma_f16_c<kPair, 2>(d, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+  }
+#elif RAFT_A_COLLECTOR == 3
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    umma_f16_c<kPair, 1>(d, a_hi + 2 * k, b_hi + 2 * k, idesc, (!first || k > 0) ? 1u : 0u);
+    umma_f16_c<kPair, 2>(d, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+    umma_f16_c<kPair, 0>(d, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+  }
+#else
+#pragma unroll
+  for (int k = 0; k < 4; ++k) umma_f16_c<kPair, 0>(d, a_hi + 2 * k, b_hi + 2 * k, idesc, (!first || k > 0) ? 1u : 0u);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) umma_f16_c<kPair, 0>(d, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) umma_f16_c<kPair, 0>(d, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+#endif
+}
+
 // 32 lanes x 32 consecutive fp32 columns: thread i of the warp gets lane (base_lane + i).
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(

@@ -553,13 +553,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarpsConv, 1) conv_tc_kernel(con
                 const uint64_t a_lo = make_desc_sw128(sa + kARow3Bytes / 2 + dx * 128);
                 const uint64_t b_hi = make_desc_sw128(sa + kARow3Bytes + dx * b_bytes);
                 const uint64_t b_lo = make_desc_sw128(sa + kARow3Bytes + (3 + dx) * b_bytes);
-#pragma unroll
-                for (int k = 0; k < kChunkK / 16; ++k)
-                  umma_f16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (!first || dx > 0 || k > 0) ? 1u : 0u);
-#pragma unroll
-                for (int k = 0; k < kChunkK / 16; ++k) umma_f16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
-#pragma unroll
-                for (int k = 0; k < kChunkK / 16; ++k) umma_f16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+                umma_chunk3<false>(d_tmem, a_hi, a_lo, b_hi, b_lo, idesc, first != 0 && dx == 0);
               }
             } else {
               const uint64_t a_hi = make_desc_sw128(sa);
@@ -569,13 +563,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarpsConv, 1) conv_tc_kernel(con
 #if defined(RAFT_TC_EXP) && (RAFT_TC_EXP & 1)        // experiment: no MMAs, only the commits
               if (sa != 0xffffffffu) goto tc_exp_skip_mma;
 #endif
-#pragma unroll
-              for (int k = 0; k < kChunkK / 16; ++k)   // +32 bytes per K=16 step == +2 in 16-byte units
-                umma_f16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (!first || k > 0) ? 1u : 0u);
-#pragma unroll
-              for (int k = 0; k < kChunkK / 16; ++k) umma_f16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
-#pragma unroll
-              for (int k = 0; k < kChunkK / 16; ++k) umma_f16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+              umma_chunk3<false>(d_tmem, a_hi, a_lo, b_hi, b_lo, idesc, first != 0);   // (+32 bytes per K=16 slice == +2 in 16-byte units)
 #if defined(RAFT_TC_EXP) && (RAFT_TC_EXP & 1)
             tc_exp_skip_mma:;
 #endif

@@ -142,12 +142,7 @@ __global__ void __launch_bounds__(kCorrThreads, 1) corr_tc_kernel(const __grid_c
             const uint32_t sa = smem_u32(stages + (size_t)s * kCorrStageBytes);
             const uint64_t a_hi = make_desc_sw128(sa), a_lo = make_desc_sw128(sa + kABytes);
             const uint64_t b_hi = make_desc_sw128(sa + 2 * kABytes), b_lo = make_desc_sw128(sa + 2 * kABytes + b_lo_off);
-#pragma unroll
-            for (int k = 0; k < kChunkK / 16; ++k) umma_f16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (!first || k > 0) ? 1u : 0u);
-#pragma unroll
-            for (int k = 0; k < kChunkK / 16; ++k) umma_f16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
-#pragma unroll
-            for (int k = 0; k < kChunkK / 16; ++k) umma_f16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+            umma_chunk3<false>(d_tmem, a_hi, a_lo, b_hi, b_lo, idesc, first != 0);
             umma_commit(&empty_bar[s]);
             if (done == pend - 1) umma_commit(&acc_full[pr]);
           }

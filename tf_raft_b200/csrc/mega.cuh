@@ -295,21 +295,11 @@ __global__ void __launch_bounds__(kMegaThreads, 1) update_mega_kernel(const __gr
             const uint64_t a_hi = make_desc_sw128(sa), a_lo = make_desc_sw128(sa + kABytes);
             const uint64_t b_hi = make_desc_sw128(sa + 2 * kABytes), b_lo = make_desc_sw128(sa + 2 * kABytes + b_bytes);
             if constexpr (kPair) {
-#pragma unroll
-              for (int k = 0; k < kChunkK / 16; ++k) umma2_f16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (!first || k > 0) ? 1u : 0u);
-#pragma unroll
-              for (int k = 0; k < kChunkK / 16; ++k) umma2_f16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
-#pragma unroll
-              for (int k = 0; k < kChunkK / 16; ++k) umma2_f16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+              umma_chunk3<true>(d_tmem, a_hi, a_lo, b_hi, b_lo, idesc, first != 0);
               umma2_commit(&empty_bar[s]);                     // frees the slot in BOTH CTAs once these MMAs retire
               if (done == gend - 1) umma2_commit(&acc_full[buf]);   // group complete -> promotion warps of both CTAs
             } else {
-#pragma unroll
-              for (int k = 0; k < kChunkK / 16; ++k) umma_f16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (!first || k > 0) ? 1u : 0u);
-#pragma unroll
-              for (int k = 0; k < kChunkK / 16; ++k) umma_f16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
-#pragma unroll
-              for (int k = 0; k < kChunkK / 16; ++k) umma_f16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+              umma_chunk3<false>(d_tmem, a_hi, a_lo, b_hi, b_lo, idesc, first != 0);
               umma_commit(&empty_bar[s]);                      // frees the smem slot once these MMAs retire
               if (done == gend - 1) umma_commit(&acc_full[buf]);   // group complete -> promotion warps
             }

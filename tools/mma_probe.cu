@@ -7,6 +7,18 @@
 #include "../tf_raft_b200/csrc/tmap.cuh"
 using namespace raft;
 
+#if defined(__CUDA_ARCH__)
+// A-operand collector: ::fill keeps the A tile in the tensor core's collector buffer, ::lastuse reuses it (no shared-memory read)
+__device__ __forceinline__ void umma_f16_afill(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+               "tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n}\n" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_f16_alast(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+               "tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n}\n" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+#endif
+
 __global__ void __launch_bounds__(128, 1) mma_probe(int n, int reps, int issuers, int distinct, int commit_every, long long* out) {
 #if defined(__CUDA_ARCH__)
   extern __shared__ uint8_t smem_raw[];
@@ -42,6 +54,11 @@ __global__ void __launch_bounds__(128, 1) mma_probe(int n, int reps, int issuers
       for (int i = 0; i < mine; ++i) {
         // distinct: walk the four K=16 slices of a 64-channel chunk like the real mainloop; else the same operands every time
         const uint64_t off = distinct ? (uint64_t)(2 * (i & 3)) : 0;
+        if (commit_every == -1) {                        // pairs of MMAs share A: fill, then lastuse with another B slice
+          const uint64_t offa = (uint64_t)(2 * ((i >> 1) & 3));
+          if (i & 1) umma_f16_alast(d, a0 + offa, b0 + off, idesc, 1u);
+          else umma_f16_afill(d, a0 + offa, b0 + off, idesc, i > 0 ? 1u : 0u);
+        } else
         umma_f16(d, a0 + off, b0 + off, idesc, i > 0 ? 1u : 0u);
         if (commit_every > 0 && (i + 1) % commit_every == 0) umma_commit(&bar[2 + warp]);   // like the mainloop: frees a stage
       }
@@ -66,7 +83,7 @@ int main() {
   printf("%5s %8s %9s %8s %14s %16s %12s\n", "N", "issuers", "operands", "commit/", "issue cyc/MMA", "complete cyc/MMA", "pipe N/2");
   for (int n : {16, 32, 64, 128, 192, 256})
     for (int issuers : {1, 2})
-      for (int commit_every : {0, 12, 24})
+      for (int commit_every : {0, -1})
       for (int distinct : {1}) {
         const int reps = 4080;
         mma_probe<<<1, 128, 100 * 1024>>>(n, reps, issuers, distinct, commit_every, out);

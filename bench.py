@@ -37,7 +37,7 @@ CONFIGS = {
                   workload='RAFT training step, batch 4 per GPU (32 over 8 GPUs), synthetic FlyingChairs 384x512, iters=12, '
                            'AdamW + one-cycle LR + global-norm clip, NCCL gradient all-reduce (BASELINE.json configs[3])'),
 }
-METRIC = 'frame-pairs/sec at 448x512 iters=12; final-flow max-abs vs ref'
+METRIC = 'frame-pairs/sec at 448\u00d7512 iters=12; final-flow max-abs vs ref'        # BASELINE.json's string, verbatim (\u00d7 = multiplication sign)
 N_ROTATE = 12            # distinct input batches cycled through: 12 x 2 x 11 MB = 264 MB > 126 MB L2
 
 # Algorithmic work of BasicUpdateBlock per feature-grid pixel (update.py:128-153)

@@ -11,8 +11,10 @@ Object-graph checkpoints name a variable `<attribute path>/.ATTRIBUTES/VARIABLE_
 `Sequential` appear as `layer_with_weights-N` (N counts only the layers that own weights).
 
 PARITY NOTE: TensorFlow is not installable in this environment, so neither the reader nor the key mapping has been run
-against a file written by TensorFlow itself; `tests/test_checkpoint.py` round-trips files produced by the writer below
-(which follows the same format description) and checks the key mapping on the reference's attribute tree.
+against a file written by TensorFlow itself; `tests/test_checkpoint.py` pins the reader on an index assembled byte by byte
+from the format description (independent CRC, prefix compression, several restart points, two data blocks), checks that the
+writer below produces exactly such bytes, round-trips files through both, and checks the key mapping on the reference's
+attribute tree.
 """
 import os
 import struct
